@@ -1,0 +1,235 @@
+"""Host-side mirror of the reference's pybind module `diff_gaussian_rasterization._C`.
+
+Same four entry points, argument order and return tuples as
+submodules/diff-gaussian-rasterization/ext.cpp:15-20 + rasterize_points.h:18-88, implemented on
+top of the C-ABI (include/grpg_b200.h) through ctypes.  PyTorch is used only for device memory
+and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Tuple
+
+import torch
+
+from . import _lib
+
+NUM_CHANNELS = 3
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("gaussianrpg_b200 needs a CUDA device (sm_100a); there is no CPU path")
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    """contiguous float32 view on the GPU, as the reference's `.contiguous().data<float>()` demands."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t) -> int | None:
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RuntimeError(_lib.last_error())
+
+
+def _layouts(P: int, R: int, W: int, H: int):
+    lib = _lib.load()
+    g, b, i = _lib.GeomLayout(), _lib.BinningLayout(), _lib.ImageLayout()
+    lib.grpg_get_geometry_layout(P, C.byref(g))
+    lib.grpg_get_binning_layout(R, C.byref(b))
+    lib.grpg_get_image_layout(W, H, C.byref(i))
+    return g, b, i
+
+
+def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
+                        cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
+                        degree, campos, prefiltered, debug
+                        ) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
+                                   torch.Tensor, torch.Tensor, torch.Tensor]:
+    """RasterizeGaussiansCUDA (rasterize_points.cu:35-124).
+
+    Returns (num_rendered, color[3,H,W], depth[1,H,W], alpha[1,H,W], semantic[S,H,W], radii[P],
+    geomBuffer, binningBuffer, imgBuffer).
+    """
+    if means3D.ndim != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:58-60
+    _require_cuda()
+    lib = _lib.load()
+    dev = means3D.device
+    P, H, W = int(means3D.shape[0]), int(image_height), int(image_width)
+    S = int(semantics.shape[1]) if semantics is not None and semantics.ndim == 2 else 0
+    M = int(sh.shape[1]) if sh is not None and sh.numel() != 0 else 0
+
+    f32 = dict(dtype=torch.float32, device=dev)
+    u8 = dict(dtype=torch.uint8, device=dev)
+    if P == 0:  # rasterize_points.cu:70-74,86
+        return (0, torch.zeros((NUM_CHANNELS, H, W), **f32), torch.zeros((1, H, W), **f32),
+                torch.zeros((1, H, W), **f32), torch.zeros((S, H, W), **f32),
+                torch.zeros((0,), dtype=torch.int32, device=dev), torch.empty(0, **u8), torch.empty(0, **u8),
+                torch.empty(0, **u8))
+
+    means3D_c, opacity_c = _f32(means3D), _f32(opacity)
+    keep = [means3D_c, opacity_c]  # keeps converted temporaries alive until the launches are queued
+
+    def opt(t):
+        if t is None or t.numel() == 0:
+            return None
+        t = _f32(t)
+        keep.append(t)
+        return t
+
+    sh_c, colors_c, sem_c = opt(sh), opt(colors), opt(semantics)
+    scales_c, rot_c, cov_c = opt(scales), opt(rotations), opt(cov3D_precomp)
+    bg_c, view_c, proj_c, cam_c = _f32(background), _f32(viewmatrix), _f32(projmatrix), _f32(campos)
+    keep += [bg_c, view_c, proj_c, cam_c]
+
+    # every pixel / Gaussian row is written by the kernels: no zero fill needed
+    out_color = torch.empty((NUM_CHANNELS, H, W), **f32)
+    out_depth = torch.empty((1, H, W), **f32)
+    out_alpha = torch.empty((1, H, W), **f32)
+    out_semantic = torch.empty((S, H, W), **f32)
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+
+    gl, _, il = _layouts(P, 0, W, H)
+    geom = torch.empty(gl.total_bytes, **u8)
+    img = torch.empty(il.total_bytes, **u8)
+
+    a = _lib.ForwardArgs()
+    a.P, a.D, a.M, a.S = P, int(degree), M, S
+    a.width, a.height = W, H
+    a.tan_fovx, a.tan_fovy, a.scale_modifier = float(tan_fovx), float(tan_fovy), float(scale_modifier)
+    a.prefiltered, a.debug = int(bool(prefiltered)), int(bool(debug))
+    a.background, a.means3D, a.shs, a.colors_precomp = _ptr(bg_c), _ptr(means3D_c), _ptr(sh_c), _ptr(colors_c)
+    a.semantics, a.opacities = _ptr(sem_c), _ptr(opacity_c)
+    a.scales, a.rotations, a.cov3D_precomp = _ptr(scales_c), _ptr(rot_c), _ptr(cov_c)
+    a.viewmatrix, a.projmatrix, a.cam_pos = _ptr(view_c), _ptr(proj_c), _ptr(cam_c)
+    a.out_color, a.out_depth, a.out_alpha = out_color.data_ptr(), out_depth.data_ptr(), out_alpha.data_ptr()
+    a.out_semantic = _ptr(out_semantic)
+    a.radii = radii.data_ptr()
+    a.geom_ws, a.image_ws, a.binning_ws = geom.data_ptr(), img.data_ptr(), None
+    a.stream = _stream()
+
+    with torch.cuda.device(dev):
+        n = C.c_int(0)
+        _check(lib.grpg_forward_geometry(C.byref(a), C.byref(n)))
+        R = int(n.value)
+        bl = _lib.BinningLayout()
+        lib.grpg_get_binning_layout(R, C.byref(bl))
+        binning = torch.empty(bl.total_bytes if R > 0 else 0, **u8)
+        a.binning_ws = _ptr(binning)
+        _check(lib.grpg_forward_render(C.byref(a), R))
+    return R, out_color, out_depth, out_alpha, out_semantic, radii, geom, binning, img
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+                                 dL_dout_depth, dL_dout_alpha, dL_dout_semantic, sh, degree, campos, geomBuffer, R,
+                                 binningBuffer, imageBuffer, alphas, semantics, debug):
+    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:126-220).
+
+    Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
+    dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4], dL_dsemantic[P,S]).
+    """
+    _require_cuda()
+    lib = _lib.load()
+    dev = means3D.device
+    P = int(means3D.shape[0])
+    H, W = int(dL_dout_color.shape[1]), int(dL_dout_color.shape[2])
+    S = int(dL_dout_semantic.shape[0])
+    M = int(sh.shape[1]) if sh is not None and sh.numel() != 0 else 0
+    f32 = dict(dtype=torch.float32, device=dev)
+
+    def out(*shape):  # fully written by grpg_backward
+        return torch.empty(shape, **f32) if P != 0 else torch.zeros(shape, **f32)
+
+    dL_dmeans3D, dL_dmeans2D, dL_dcolors = out(P, 3), out(P, 3), out(P, NUM_CHANNELS)
+    dL_ddepths, dL_dconic, dL_dopacity = out(P, 1), out(P, 2, 2), out(P, 1)
+    dL_dcov3D, dL_dsh, dL_dscales, dL_drot = out(P, 6), out(P, M, 3), out(P, 3), out(P, 4)
+    dL_dsemantic = out(P, S)
+    if P == 0:
+        return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot,
+                dL_dsemantic)
+
+    keep = []
+
+    def opt(t):
+        if t is None or t.numel() == 0:
+            return None
+        t = _f32(t)
+        keep.append(t)
+        return t
+
+    a = _lib.BackwardArgs()
+    a.P, a.D, a.M, a.S, a.R = P, int(degree), M, S, int(R)
+    a.width, a.height = W, H
+    a.tan_fovx, a.tan_fovy, a.scale_modifier, a.debug = float(tan_fovx), float(tan_fovy), float(scale_modifier), int(
+        bool(debug))
+    a.background, a.means3D = _ptr(opt(background)), _ptr(opt(means3D))
+    a.shs, a.colors_precomp, a.semantics = _ptr(opt(sh)), _ptr(opt(colors)), _ptr(opt(semantics))
+    a.alphas = _ptr(opt(alphas))
+    a.scales, a.rotations, a.cov3D_precomp = _ptr(opt(scales)), _ptr(opt(rotations)), _ptr(opt(cov3D_precomp))
+    a.viewmatrix, a.projmatrix, a.cam_pos = _ptr(opt(viewmatrix)), _ptr(opt(projmatrix)), _ptr(opt(campos))
+    radii_c = radii.contiguous()
+    a.radii = radii_c.data_ptr()
+    a.geom_ws, a.binning_ws, a.image_ws = _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer)
+    a.dL_dpix, a.dL_dpix_depth = _ptr(opt(dL_dout_color)), _ptr(opt(dL_dout_depth))
+    a.dL_dalphas, a.dL_dpix_semantic = _ptr(opt(dL_dout_alpha)), _ptr(opt(dL_dout_semantic))
+    a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = dL_dmeans2D.data_ptr(), dL_dconic.data_ptr(), dL_dopacity.data_ptr()
+    a.dL_dcolor, a.dL_ddepth, a.dL_dmean3D = dL_dcolors.data_ptr(), dL_ddepths.data_ptr(), dL_dmeans3D.data_ptr()
+    a.dL_dcov3D, a.dL_dsh = dL_dcov3D.data_ptr(), _ptr(dL_dsh)
+    a.dL_dscale, a.dL_drot, a.dL_dsemantic = dL_dscales.data_ptr(), dL_drot.data_ptr(), _ptr(dL_dsemantic)
+    grad_ws = torch.empty(lib.grpg_backward_workspace_bytes(P, S), dtype=torch.uint8, device=dev)
+    a.grad_ws = grad_ws.data_ptr()
+    a.stream = _stream()
+    with torch.cuda.device(dev):
+        _check(lib.grpg_backward(C.byref(a)))
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot, dL_dsemantic
+
+
+def mark_visible(means3D, viewmatrix, projmatrix) -> torch.Tensor:
+    """markVisible (rasterize_points.cu:222-242): bool[P], true where view-space z > 0.2."""
+    _require_cuda()
+    lib = _lib.load()
+    P = int(means3D.shape[0])
+    present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+    if P != 0:
+        m, v, p = _f32(means3D), _f32(viewmatrix), _f32(projmatrix)
+        with torch.cuda.device(means3D.device):
+            _check(lib.grpg_mark_visible(P, m.data_ptr(), v.data_ptr(), p.data_ptr(), present.data_ptr(), _stream()))
+    return present
+
+
+def rasterize_gaussians_filter(means3D, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix,
+                               tan_fovx, tan_fovy, image_height, image_width, prefiltered, debug):
+    """RasterizeGaussiansfilterCUDA (rasterize_points.cu:244-306): (radii[P] int32, means2D[P,2])."""
+    if means3D.ndim != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    _require_cuda()
+    lib = _lib.load()
+    dev = means3D.device
+    P = int(means3D.shape[0])
+    radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+    means2D = torch.zeros((P, 2), dtype=torch.float32, device=dev)
+    if P != 0:
+        m, v, p = _f32(means3D), _f32(viewmatrix), _f32(projmatrix)
+        s = _f32(scales) if scales is not None and scales.numel() else None
+        r = _f32(rotations) if rotations is not None and rotations.numel() else None
+        c = _f32(cov3D_precomp) if cov3D_precomp is not None and cov3D_precomp.numel() else None
+        with torch.cuda.device(dev):
+            _check(lib.grpg_visible_filter(P, int(image_width), int(image_height), m.data_ptr(), _ptr(s),
+                                           float(scale_modifier), _ptr(r), _ptr(c), v.data_ptr(), p.data_ptr(),
+                                           float(tan_fovx), float(tan_fovy), radii.data_ptr(), means2D.data_ptr(),
+                                           _stream()))
+    return radii, means2D

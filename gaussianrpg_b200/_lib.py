@@ -1,0 +1,108 @@
+"""ctypes view of libgrpg_b200.so -- the C-ABI declared in include/grpg_b200.h.
+
+There is deliberately no fallback: if the CUDA library is missing or fails to load, importing
+the product path raises.  (The CPU oracle under oracle/ is test infrastructure only.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libgrpg_b200.so"
+
+
+class GeomLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "total_bytes", "rec", "depth_key", "rect", "tiles_touched", "cov3d", "clamped", "sorted_idx", "offsets",
+        "scratch", "num_rendered")]
+
+
+class BinningLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("total_bytes", "point_list", "tile_keys", "scratch")]
+
+
+class ImageLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("total_bytes", "n_contrib", "ranges")]
+
+
+_fp = C.c_void_p  # device pointers cross the ABI as plain addresses
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("S", C.c_int),
+        ("width", C.c_int), ("height", C.c_int),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int), ("debug", C.c_int),
+        ("background", _fp), ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("semantics", _fp),
+        ("opacities", _fp), ("scales", _fp), ("rotations", _fp), ("cov3D_precomp", _fp),
+        ("viewmatrix", _fp), ("projmatrix", _fp), ("cam_pos", _fp),
+        ("out_color", _fp), ("out_depth", _fp), ("out_alpha", _fp), ("out_semantic", _fp), ("radii", _fp),
+        ("geom_ws", _fp), ("binning_ws", _fp), ("image_ws", _fp), ("stream", _fp),
+    ]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("S", C.c_int), ("R", C.c_int),
+        ("width", C.c_int), ("height", C.c_int),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float), ("debug", C.c_int),
+        ("background", _fp), ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("semantics", _fp),
+        ("alphas", _fp), ("scales", _fp), ("rotations", _fp), ("cov3D_precomp", _fp),
+        ("viewmatrix", _fp), ("projmatrix", _fp), ("cam_pos", _fp), ("radii", _fp),
+        ("geom_ws", _fp), ("binning_ws", _fp), ("image_ws", _fp),
+        ("dL_dpix", _fp), ("dL_dpix_depth", _fp), ("dL_dalphas", _fp), ("dL_dpix_semantic", _fp),
+        ("dL_dmean2D", _fp), ("dL_dconic", _fp), ("dL_dopacity", _fp), ("dL_dcolor", _fp), ("dL_ddepth", _fp),
+        ("dL_dmean3D", _fp), ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dscale", _fp), ("dL_drot", _fp),
+        ("dL_dsemantic", _fp), ("grad_ws", _fp), ("stream", _fp),
+    ]
+
+
+# every symbol include/grpg_b200.h declares, with its ctypes signature
+SYMBOLS = {
+    "grpg_get_geometry_layout": (C.c_int, [C.c_int, C.POINTER(GeomLayout)]),
+    "grpg_get_binning_layout": (C.c_int, [C.c_longlong, C.POINTER(BinningLayout)]),
+    "grpg_get_image_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(ImageLayout)]),
+    "grpg_forward_geometry": (C.c_int, [C.POINTER(ForwardArgs), C.POINTER(C.c_int)]),
+    "grpg_forward_render": (C.c_int, [C.POINTER(ForwardArgs), C.c_int]),
+    "grpg_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "grpg_backward": (C.c_int, [C.POINTER(BackwardArgs)]),
+    "grpg_mark_visible": (C.c_int, [C.c_int, _fp, _fp, _fp, _fp, _fp]),
+    "grpg_visible_filter": (C.c_int, [C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_float, _fp, _fp, _fp, _fp,
+                                      C.c_float, C.c_float, _fp, _fp, _fp]),
+    "grpg_debug_reference_keys": (C.c_int, [C.c_int, C.c_longlong, _fp, _fp, _fp, _fp]),
+    "grpg_last_error": (C.c_char_p, []),
+    "grpg_version": (C.c_int, []),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library once; build it in-tree first when sources are newer (needs nvcc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if os.environ.get("GRPG_NO_AUTOBUILD", "0") != "1":
+        try:
+            from . import build as _build
+            if _build.needs_build():
+                _build.build()
+        except Exception as exc:  # no nvcc on this box: fall through to the prebuilt .so
+            if not LIB_PATH.exists():
+                raise RuntimeError(f"libgrpg_b200.so is not built and cannot be built here: {exc}") from exc
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} missing -- run `python -m gaussianrpg_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError here means the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().grpg_last_error().decode("utf-8", "replace")

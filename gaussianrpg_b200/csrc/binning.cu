@@ -1,0 +1,234 @@
+// binning.cu -- ordering of Gaussian/tile instances.
+//
+// The reference emits one 64-bit key ((tile << 32) | depth bits) per Gaussian/tile overlap
+// (duplicateWithKeys, rasterizer_impl.cu:70-111) and runs a stable LSD radix sort over the
+// low 32+bit bits of R such pairs (rasterizer_impl.cu:303-311): 6 digit passes over 12 B * R.
+//
+// B200 redesign (same resulting order, ~5x fewer bytes): the depth ordering is a property of
+// the Gaussian, not of the instance.  So
+//   1. sort the P Gaussians once by (depth bits, id)          -- 4 passes over 8 B * P
+//   2. prefix-sum tile counts in that order                    -- replaces InclusiveSum (:280)
+//   3. emit instances in depth order, balanced over warps      -- replaces duplicateWithKeys
+//   4. stable-sort instances by tile id only (14 bits at 1920x1280 -> 2 passes over 8 B * R)
+// A stable sort by tile of a depth-ordered sequence is exactly the (tile, depth, id) order of
+// the reference; ties on equal depth keep ascending Gaussian id in both.
+#include "radix_sort.cuh"
+
+namespace grpg {
+
+// ---- 2. exclusive scan of tiles_touched in sorted order (decoupled look-back) ------------
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_TILE = 256 * SCAN_IPT;
+constexpr unsigned long long SC_FLAG_AGG = 1ull << 62;
+constexpr unsigned long long SC_FLAG_PREFIX = 2ull << 62;
+constexpr unsigned long long SC_FLAG_MASK = 3ull << 62;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restrict__ sorted_idx,
+                                                         const uint32_t* __restrict__ tiles_touched, uint32_t P,
+                                                         uint32_t* __restrict__ offsets,
+                                                         unsigned long long* __restrict__ status /*[tiles+1]*/,
+                                                         uint32_t* __restrict__ tile_counter,
+                                                         unsigned long long* __restrict__ total_out) {
+    __shared__ uint32_t s_scan[8];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    uint32_t v[SCAN_IPT];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_IPT; ++i) {
+        uint32_t j = base + i;
+        v[i] = j < P ? tiles_touched[sorted_idx[j]] : 0u;
+        sum += v[i];
+    }
+    uint32_t block_total;
+    uint32_t texcl = block_exclusive_scan_256(sum, s_scan, &block_total);
+    if (threadIdx.x == 0) {
+        st_volatile_u64(status + tile, (unsigned long long)block_total | (tile == 0 ? SC_FLAG_PREFIX : SC_FLAG_AGG));
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            while (true) {
+                unsigned long long s = ld_volatile_u64(status + t);
+                unsigned long long f = s & SC_FLAG_MASK;
+                if (f == 0) continue;
+                excl += s & ~SC_FLAG_MASK;
+                if (f == SC_FLAG_PREFIX) break;
+                --t;
+            }
+            st_volatile_u64(status + tile, (excl + block_total) | SC_FLAG_PREFIX);
+        }
+        s_excl = excl;
+        if ((tile + 1) * (unsigned long long)SCAN_TILE >= P) *total_out = excl + block_total;
+    }
+    __syncthreads();
+    uint32_t run = (uint32_t)s_excl + texcl;
+#pragma unroll
+    for (int i = 0; i < SCAN_IPT; ++i) {
+        uint32_t j = base + i;
+        if (j < P) offsets[j] = run;
+        run += v[i];
+    }
+}
+
+// ---- 3. instance emission ------------------------------------------------------------------
+// One warp owns 32 consecutive depth-sorted Gaussians and writes their instances as one
+// contiguous run, 32 instances per step, so a splat covering thousands of tiles is spread
+// over the whole warp instead of one thread (reference: one thread loops over all its tiles,
+// rasterizer_impl.cu:98-109).
+__global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __restrict__ sorted_idx,
+                                                             const uint32_t* __restrict__ offsets,
+                                                             const uint2* __restrict__ rect, uint32_t P,
+                                                             uint32_t grid_x, uint32_t* __restrict__ inst_tile,
+                                                             uint32_t* __restrict__ inst_gauss) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t pos = (blockIdx.x * blockDim.x + threadIdx.x);  // sorted position of this lane's Gaussian
+    uint32_t g = 0, off = 0, x0 = 0, y0 = 0, w = 0, cnt = 0;
+    if (pos < P) {
+        g = sorted_idx[pos];
+        off = offsets[pos];
+        uint2 r = rect[g];
+        x0 = r.x & 0xffffu; y0 = r.y & 0xffffu;
+        w = (r.x >> 16) - x0;
+        cnt = w * ((r.y >> 16) - y0);
+    }
+    const uint32_t run_start = __shfl_sync(0xffffffffu, off, 0);
+    // exclusive offset inside the warp's run; lanes past P never own an instance
+    const uint32_t rel = pos < P ? off - run_start : 0xFFFFFFFFu;
+    const uint32_t run_len = __reduce_max_sync(0xffffffffu, pos < P ? rel + cnt : 0u);
+    for (uint32_t k0 = 0; k0 < run_len; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        // owner = last lane whose rel <= k (rel is non-decreasing)
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            uint32_t probe = __shfl_sync(0xffffffffu, rel, (owner + step) & 31);
+            if (owner + step < 32 && probe <= k) owner += step;
+        }
+        const uint32_t o_rel = __shfl_sync(0xffffffffu, rel, owner);
+        const uint32_t o_w = __shfl_sync(0xffffffffu, w, owner);
+        const uint32_t o_x0 = __shfl_sync(0xffffffffu, x0, owner);
+        const uint32_t o_y0 = __shfl_sync(0xffffffffu, y0, owner);
+        const uint32_t o_g = __shfl_sync(0xffffffffu, g, owner);
+        if (k < run_len) {
+            const uint32_t m = k - o_rel;
+            const uint32_t ty = m / o_w, tx = m - ty * o_w;
+            inst_tile[run_start + k] = (o_y0 + ty) * grid_x + (o_x0 + tx);
+            inst_gauss[run_start + k] = o_g;
+        }
+    }
+}
+
+// ---- 5. tile ranges (identifyTileRanges, rasterizer_impl.cu:116-138) -----------------------
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ tile_keys, uint32_t R,
+                                                          uint2* __restrict__ ranges) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t cur = tile_keys[i];
+    if (i == 0) ranges[cur].x = 0;
+    else {
+        const uint32_t prev = tile_keys[i - 1];
+        if (cur != prev) { ranges[prev].y = i; ranges[cur].x = i; }
+    }
+    if (i == R - 1) ranges[cur].y = R;
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
+__global__ void __launch_bounds__(256) reference_keys_kernel(const uint32_t* __restrict__ point_list,
+                                                             const uint32_t* __restrict__ tile_keys,
+                                                             const Rec* __restrict__ rec, uint32_t R,
+                                                             unsigned long long* __restrict__ keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    keys[i] = ((unsigned long long)tile_keys[i] << 32) | __float_as_uint(rec[point_list[i]].c.w);
+}
+
+// ---- host orchestration ----------------------------------------------------------------------
+// scratch layout inside geom_ws.scratch: [keys_b P][vals_b P][sort aux][scan status][counters]
+size_t geom_scratch_bytes(int P) {
+    size_t b = 0;
+    b += align_up((size_t)P * 4, 256) * 2;
+    b += align_up((size_t)SORT_MAX_PASSES * (256 + 64) * 4 + (size_t)SORT_MAX_PASSES * sort_num_tiles(P) * 256 * 4, 256);
+    b += align_up(((size_t)(P + SCAN_TILE - 1) / SCAN_TILE + 2) * 8, 256);
+    b += 256;  // scan tile counter + total
+    return b;
+}
+size_t binning_scratch_bytes(long long R) {
+    size_t b = 0;
+    b += align_up((size_t)R * 4, 256) * 2;
+    b += align_up((size_t)SORT_MAX_PASSES * (256 + 64) * 4 + (size_t)SORT_MAX_PASSES * sort_num_tiles(R) * 256 * 4, 256);
+    return b;
+}
+
+// Steps 1-2.  depth_key is consumed (left sorted); sorted_idx receives the permutation.
+void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, const uint32_t* tiles_touched,
+                              uint32_t* offsets, void* scratch, unsigned long long* num_rendered_dev, int num_sms,
+                              cudaStream_t stream) {
+    char* p = (char*)scratch;
+    uint32_t* keys_b = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
+    uint32_t* vals_b = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
+    uint32_t* aux = (uint32_t*)p;
+    p += align_up((size_t)SORT_MAX_PASSES * (256 + 64) * 4 + (size_t)SORT_MAX_PASSES * sort_num_tiles(P) * 256 * 4, 256);
+    unsigned long long* status = (unsigned long long*)p;
+    size_t scan_tiles = ((size_t)P + SCAN_TILE - 1) / SCAN_TILE;
+    p += align_up((scan_tiles + 2) * 8, 256);
+    uint32_t* scan_counter = (uint32_t*)p;
+
+    iota_kernel<<<(P + 255) / 256, 256, 0, stream>>>(sorted_idx, (uint32_t)P);
+    bool in_a = onesweep_sort_pairs(depth_key, sorted_idx, keys_b, vals_b, P, 32, aux, num_sms, stream);
+    if (!in_a) {  // 32 bits -> 4 passes -> always lands back in the a-buffers; kept for safety
+        cudaMemcpyAsync(depth_key, keys_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
+        cudaMemcpyAsync(sorted_idx, vals_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
+    }
+    cudaMemsetAsync(status, 0, (scan_tiles + 2) * 8 + 256, stream);
+    scan_tiles_kernel<<<(unsigned)scan_tiles, 256, 0, stream>>>(sorted_idx, tiles_touched, (uint32_t)P, offsets, status,
+                                                                 scan_counter, num_rendered_dev);
+}
+
+// Steps 3-5.  Final order lands in (tile_keys, point_list).
+void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tiles, const uint32_t* sorted_idx,
+                          const uint32_t* offsets, const uint2* rect, uint32_t* tile_keys, uint32_t* point_list,
+                          void* scratch, uint2* ranges, int num_sms, cudaStream_t stream) {
+    cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), stream);
+    if (R <= 0) return;
+    char* p = (char*)scratch;
+    uint32_t* keys_b = (uint32_t*)p; p += align_up((size_t)R * 4, 256);
+    uint32_t* vals_b = (uint32_t*)p; p += align_up((size_t)R * 4, 256);
+    uint32_t* aux = (uint32_t*)p;
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)num_tiles) ++bits;
+    SortPlan plan = make_sort_plan(bits);
+    // choose the start buffer so that the last pass writes (tile_keys, point_list)
+    const bool start_in_final = (plan.passes % 2) == 0;
+    uint32_t* k0 = start_in_final ? tile_keys : keys_b;
+    uint32_t* v0 = start_in_final ? point_list : vals_b;
+    uint32_t* k1 = start_in_final ? keys_b : tile_keys;
+    uint32_t* v1 = start_in_final ? vals_b : point_list;
+    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(sorted_idx, offsets, rect, (uint32_t)P, grid_x, k0, v0);
+    onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream);
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(tile_keys, (uint32_t)R, ranges);
+}
+
+void launch_reference_keys(long long R, const uint32_t* point_list, const uint32_t* tile_keys, const Rec* rec,
+                           unsigned long long* keys, cudaStream_t stream) {
+    if (R <= 0) return;
+    reference_keys_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(point_list, tile_keys, rec, (uint32_t)R, keys);
+}
+
+}  // namespace grpg

@@ -1,0 +1,218 @@
+// blend_bwd.cu -- per-tile back-to-front replay producing per-Gaussian 2D gradients.
+//
+// Behavioural spec: reference renderCUDA backward (cuda_rasterizer/backward.cu:415-641):
+// T starts at T_final = 1 - alpha_out (:468), instances behind a pixel's last contributor are
+// skipped (:530-532), the 0.99 clamp is straight-through (:543,618), dL_dmean2D is in NDC units
+// with a third |gx|+|gy| channel (:625-628), dL_dconic.z is unused (:633-635).
+//
+// B200 design.  The reference issues 11+S global float atomics per (pixel, Gaussian) hit.
+// Here a warp owns an 8x4 pixel block, culls instances with the same conservative footprint
+// as the forward, reduces the per-lane partials with shuffles and issues ONE vector of
+// atomics per (warp, Gaussian) -- lanes 0..10 each add one component of the 48-byte gradient
+// record, so the 11 adds leave the SM as a single coalesced RED request.
+#include "grpg_common.cuh"
+
+namespace grpg {
+
+constexpr int BWD_BATCH = 256;
+constexpr int GREC = 12;  // floats per Gaussian in the gradient record
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int SB>
+__global__ void __launch_bounds__(256) blend_bwd_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const Rec* __restrict__ rec,
+    const float* __restrict__ semantics, int S, int W, int H, const float* __restrict__ bg_color,
+    const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+    const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dalphas,
+    const float* __restrict__ dL_dpixel_semantics, float* __restrict__ grad_rec /*[P][12]*/,
+    float* __restrict__ dL_dsemantics /*[P][S]*/) {
+    __shared__ float4 s_a[BWD_BATCH];
+    __shared__ float4 s_b[BWD_BATCH];
+    __shared__ float4 s_c[BWD_BATCH];
+    __shared__ uint32_t s_id[BWD_BATCH];
+    __shared__ int s_maxlast[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
+    const uint32_t tile = blockIdx.y * tiles_x + blockIdx.x;
+    const int bx0 = blockIdx.x * GRPG_TILE + (warp & 1) * 8;
+    const int by0 = blockIdx.y * GRPG_TILE + (warp >> 1) * 4;
+    const int pix_x = bx0 + (lane & 7), pix_y = by0 + (lane >> 3);
+    const bool inside = pix_x < W && pix_y < H;
+    const float pxf = (float)pix_x, pyf = (float)pix_y;
+    const float bx_lo = (float)bx0, bx_hi = (float)(bx0 + 7), by_lo = (float)by0, by_hi = (float)(by0 + 3);
+    const size_t hw = (size_t)H * W;
+    const size_t pid = (size_t)pix_y * W + pix_x;
+
+    const uint2 range = ranges[tile];
+    const int n_inst = (int)(range.y - range.x);
+
+    const float T_final = inside ? 1.0f - alphas[pid] : 0.0f;
+    float T = T_final;
+    const int last_contributor = inside ? (int)n_contrib[pid] : 0;
+
+    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, dpix_depth = 0.f, dpix_alpha = 0.f;
+    float dsem[SB > 0 ? SB : 1];
+    if (inside) {
+        dpix0 = dL_dpixels[pid]; dpix1 = dL_dpixels[hw + pid]; dpix2 = dL_dpixels[2 * hw + pid];
+        dpix_depth = dL_dpixel_depths[pid];
+        dpix_alpha = dL_dalphas[pid];
+    }
+#pragma unroll
+    for (int i = 0; i < (SB > 0 ? SB : 1); ++i)
+        dsem[i] = (SB > 0 && inside && i < S) ? dL_dpixel_semantics[(size_t)i * hw + pid] : 0.f;
+    const float bg_dot_dpixel = bg_color[0] * dpix0 + bg_color[1] * dpix1 + bg_color[2] * dpix2;
+
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc_depth = 0.f, acc_alpha = 0.f;
+    float lastc0 = 0.f, lastc1 = 0.f, lastc2 = 0.f, last_depth = 0.f, last_alpha = 0.f;
+    float acc_sem[SB > 0 ? SB : 1], last_sem[SB > 0 ? SB : 1];
+#pragma unroll
+    for (int i = 0; i < (SB > 0 ? SB : 1); ++i) { acc_sem[i] = 0.f; last_sem[i] = 0.f; }
+
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    // nothing behind the deepest last-contributor of the tile can receive gradient
+    int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (lane == 0) s_maxlast[warp] = wmax;
+    __syncthreads();
+    int tile_last = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tile_last = max(tile_last, s_maxlast[w]);
+    tile_last = min(tile_last, n_inst);
+
+    for (int top = tile_last; top > 0; top -= BWD_BATCH) {
+        const int cnt = min(BWD_BATCH, top);
+        __syncthreads();
+        if (tid < cnt) {
+            // slot t holds 0-based position top-1-t: ascending slot = back-to-front
+            const uint32_t id = point_list[range.x + top - 1 - tid];
+            const float4* r = reinterpret_cast<const float4*>(rec + id);
+            s_a[tid] = __ldg(r);
+            s_b[tid] = __ldg(r + 1);
+            s_c[tid] = __ldg(r + 2);
+            s_id[tid] = id;
+        }
+        __syncthreads();
+        if (wmax <= top - cnt) continue;  // every pixel of this warp ended before this batch
+
+        for (int g0 = 0; g0 < cnt; g0 += 32) {
+            const int j = g0 + lane;
+            bool hit = false;
+            if (j < cnt) {
+                const float4 a = s_a[j];
+                hit = (a.x + a.z >= bx_lo) && (a.x - a.z <= bx_hi) && (a.y + a.w >= by_lo) && (a.y - a.w <= by_hi);
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int k = g0 + __ffs(m) - 1;
+                m &= m - 1;
+                const int pos = top - 1 - k;  // 0-based position in the tile's range
+                const float4 a = s_a[k];
+                const float4 b = s_b[k];
+                const float dx = a.x - pxf, dy = a.y - pyf;
+                const float power = ffma(ffma(dx, fmul(dx, b.x), fmul(dy, fmul(dy, b.z))), -0.5f, -fmul(dy, fmul(dx, b.y)));
+                const float G = expf(power);
+                const float alpha = fminf(0.99f, b.w * G);
+                const bool active = (pos < last_contributor) && !(power > 0.0f) && (alpha >= 1.0f / 255.0f);
+                if (!__any_sync(0xffffffffu, active)) continue;
+
+                float g_mx = 0.f, g_my = 0.f, g_mabs = 0.f, g_cx = 0.f, g_cy = 0.f, g_cw = 0.f, g_op = 0.f;
+                float g_c0 = 0.f, g_c1 = 0.f, g_c2 = 0.f, g_d = 0.f;
+                float g_sem[SB > 0 ? SB : 1];
+#pragma unroll
+                for (int i = 0; i < (SB > 0 ? SB : 1); ++i) g_sem[i] = 0.f;
+                if (active) {
+                    const float4 c = s_c[k];
+                    T = T / (1.f - alpha);
+                    const float w_at = alpha * T;
+                    float dL_dopa = 0.f;
+                    acc0 = last_alpha * lastc0 + (1.f - last_alpha) * acc0; lastc0 = c.x;
+                    dL_dopa += (c.x - acc0) * dpix0; g_c0 = w_at * dpix0;
+                    acc1 = last_alpha * lastc1 + (1.f - last_alpha) * acc1; lastc1 = c.y;
+                    dL_dopa += (c.y - acc1) * dpix1; g_c1 = w_at * dpix1;
+                    acc2 = last_alpha * lastc2 + (1.f - last_alpha) * acc2; lastc2 = c.z;
+                    dL_dopa += (c.z - acc2) * dpix2; g_c2 = w_at * dpix2;
+                    if (SB > 0) {
+                        const float* sp = semantics + (size_t)s_id[k] * S;
+#pragma unroll
+                        for (int i = 0; i < SB; ++i) {
+                            if (i < S) {
+                                const float sv = __ldg(sp + i);
+                                acc_sem[i] = last_alpha * last_sem[i] + (1.f - last_alpha) * acc_sem[i];
+                                last_sem[i] = sv;
+                                dL_dopa += (sv - acc_sem[i]) * dsem[i];
+                                g_sem[i] = w_at * dsem[i];
+                            }
+                        }
+                    }
+                    acc_depth = last_alpha * last_depth + (1.f - last_alpha) * acc_depth; last_depth = c.w;
+                    dL_dopa += (c.w - acc_depth) * dpix_depth; g_d = w_at * dpix_depth;
+                    acc_alpha = last_alpha + (1.f - last_alpha) * acc_alpha;
+                    dL_dopa += (1.f - acc_alpha) * dpix_alpha;
+                    dL_dopa *= T;
+                    last_alpha = alpha;
+                    dL_dopa += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                    const float dL_dG = b.w * dL_dopa;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * b.x - gdy * b.y;
+                    const float dG_ddely = -gdy * b.z - gdx * b.y;
+                    g_mx = dL_dG * dG_ddelx * ddelx_dx;
+                    g_my = dL_dG * dG_ddely * ddely_dy;
+                    g_mabs = fabsf(g_mx) + fabsf(g_my);
+                    g_cx = -0.5f * gdx * dx * dL_dG;
+                    g_cy = -0.5f * gdx * dy * dL_dG;
+                    g_cw = -0.5f * gdy * dy * dL_dG;
+                    g_op = G * dL_dopa;
+                }
+                // warp reduction, then one vector of atomics per (warp, Gaussian)
+                g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_mabs = warp_sum(g_mabs);
+                g_cx = warp_sum(g_cx); g_cy = warp_sum(g_cy); g_cw = warp_sum(g_cw);
+                g_op = warp_sum(g_op);
+                g_c0 = warp_sum(g_c0); g_c1 = warp_sum(g_c1); g_c2 = warp_sum(g_c2);
+                g_d = warp_sum(g_d);
+                float mine = 0.f;
+                switch (lane) {
+                    case 0: mine = g_mx; break;   case 1: mine = g_my; break;  case 2: mine = g_mabs; break;
+                    case 3: mine = g_cx; break;   case 4: mine = g_cy; break;  case 5: mine = g_cw; break;
+                    case 6: mine = g_op; break;   case 7: mine = g_c0; break;  case 8: mine = g_c1; break;
+                    case 9: mine = g_c2; break;   case 10: mine = g_d; break;  default: break;
+                }
+                const uint32_t gid = s_id[k];
+                if (lane < 11) atomicAdd(grad_rec + (size_t)gid * GREC + lane, mine);
+                if (SB > 0) {
+#pragma unroll
+                    for (int i = 0; i < SB; ++i) {
+                        if (i < S) {
+                            const float v = warp_sum(g_sem[i]);
+                            if (lane == 0) atomicAdd(dL_dsemantics + (size_t)gid * S + i, v);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const uint32_t* point_list, const Rec* rec,
+                      const uint32_t* n_contrib, float* grad_rec, cudaStream_t stream) {
+    const dim3 grid((a->width + GRPG_TILE - 1) / GRPG_TILE, (a->height + GRPG_TILE - 1) / GRPG_TILE, 1);
+    const int S = a->S;
+#define GRPG_BWD_LAUNCH(SBV)                                                                                      \
+    blend_bwd_kernel<SBV><<<grid, 256, 0, stream>>>(ranges, point_list, rec, a->semantics, S, a->width, a->height,  \
+                                                     a->background, a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth, \
+                                                     a->dL_dalphas, a->dL_dpix_semantic, grad_rec, a->dL_dsemantic)
+    if (S == 0) GRPG_BWD_LAUNCH(0);
+    else if (S <= 4) GRPG_BWD_LAUNCH(4);
+    else if (S <= 8) GRPG_BWD_LAUNCH(8);
+    else if (S <= 16) GRPG_BWD_LAUNCH(16);
+    else GRPG_BWD_LAUNCH(32);
+#undef GRPG_BWD_LAUNCH
+}
+
+}  // namespace grpg

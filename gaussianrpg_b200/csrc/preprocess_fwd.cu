@@ -1,0 +1,365 @@
+// preprocess_fwd.cu -- per-Gaussian forward stage: near cull, EWA projection, conic, screen
+// radius, tile rectangle, SH -> RGB, plus the conservative alpha>=1/255 footprint used by the
+// blend kernels for warp-level culling.
+//
+// Behavioural spec: reference preprocessCUDA (cuda_rasterizer/forward.cu:155-256) with
+// in_frustum (auxiliary.h:139-164), computeCov3D (forward.cu:118-152), computeCov2D
+// (forward.cu:74-113), computeColorFromSH (forward.cu:20-71), ndc2Pix/getRect
+// (auxiliary.h:41-56).  Rounding sequence: see DESIGN.md "arithmetic contract".
+#include <cstdio>
+#include "grpg_common.cuh"
+
+namespace grpg {
+
+struct ProjOut {
+    float depth;      // view-space z
+    float px, py;     // pixel centre
+    float a, b, c;    // cov2D incl. +0.3 blur
+    float conx, cony, conz;
+    int radius;
+    uint32_t xmin, xmax, ymin, ymax;
+    float cov3d[6];
+    bool visible;
+};
+
+__device__ __forceinline__ void cov3d_from_scale_rot(const float sx_in, const float sy_in, const float sz_in, float mod,
+                                                     float r, float x, float y, float z, float* cov3D) {
+    // forward.cu:118-152 (quaternion used un-normalised, :127)
+    const float sx = fmul(sx_in, mod), sy = fmul(sy_in, mod), sz = fmul(sz_in, mod);
+    const float xz = fmul(x, z), rx = fmul(r, x), rz = fmul(r, z), yy = fmul(y, y), zz = fmul(z, z);
+    const float xz_p_ry = ffma(r, y, xz), xz_m_ry = ffma(-r, y, xz);
+    const float yz_m_rx = ffma(y, z, -rx), yz_p_rx = ffma(y, z, rx);
+    const float xy_m_rz = ffma(x, y, -rz), xy_p_rz = ffma(x, y, rz);
+    const float xx_yy = ffma(x, x, yy), yy_zz = fadd(yy, zz), xx_zz = ffma(x, x, zz);
+    // R[c][r] (column c, row r) of the glm matrix built at forward.cu:134-138
+    const float R00 = fadd(-fadd(yy_zz, yy_zz), 1.0f), R01 = fadd(xy_m_rz, xy_m_rz), R02 = fadd(xz_p_ry, xz_p_ry);
+    const float R10 = fadd(xy_p_rz, xy_p_rz), R11 = fadd(-fadd(xx_zz, xx_zz), 1.0f), R12 = fadd(yz_m_rx, yz_m_rx);
+    const float R20 = fadd(xz_m_ry, xz_m_ry), R21 = fadd(yz_p_rx, yz_p_rx), R22 = fadd(-fadd(xx_yy, xx_yy), 1.0f);
+    // M = S * R  ->  M[c][r] = s_r * R[c][r]
+    const float M00 = fmul(sx, R00), M01 = fmul(sy, R01), M02 = fmul(sz, R02);
+    const float M10 = fmul(sx, R10), M11 = fmul(sy, R11), M12 = fmul(sz, R12);
+    const float M20 = fmul(sx, R20), M21 = fmul(sy, R21), M22 = fmul(sz, R22);
+    // Sigma = M^T M : Sigma[c][r] = sum_k M[r][k] * M[c][k]
+    cov3D[0] = dot3(M00, M00, M01, M01, M02, M02);
+    cov3D[1] = dot3(M10, M00, M11, M01, M12, M02);
+    cov3D[2] = dot3(M20, M00, M21, M01, M22, M02);
+    cov3D[3] = dot3(M10, M10, M11, M11, M12, M12);
+    cov3D[4] = dot3(M20, M10, M21, M11, M22, M12);
+    cov3D[5] = dot3(M20, M20, M21, M21, M22, M22);
+}
+
+// Everything that determines visibility, keys and the 2D footprint of one Gaussian.
+__device__ __forceinline__ void project_gaussian(float x, float y, float z, const float* __restrict__ v,
+                                                 const float* __restrict__ m, const float* cov3D, int W, int H,
+                                                 float tan_fovx, float tan_fovy, float focal_x, float focal_y,
+                                                 uint32_t grid_x, uint32_t grid_y, ProjOut& o) {
+    o.visible = false;
+    o.radius = 0;
+    const float tz = xform_row(v, 2, x, y, z);
+    o.depth = tz;
+    if (tz <= 0.2f) return;  // auxiliary.h:154 (NaN passes, as in the reference)
+
+    const float hx = xform_row(m, 0, x, y, z);
+    const float hy = xform_row(m, 1, x, y, z);
+    const float hw = xform_row(m, 3, x, y, z);
+    const float p_w = frcp(fadd(hw, 0.0000001f));
+    const float ndc_x = fmul(hx, p_w), ndc_y = fmul(hy, p_w);
+
+    // computeCov2D, forward.cu:74-113
+    const float tx = xform_row(v, 0, x, y, z);
+    const float ty = xform_row(v, 1, x, y, z);
+    const float limx = fmul(tan_fovx, 1.3f), limy = fmul(tan_fovy, 1.3f);
+    const float cx = fminf(fmaxf(fdiv(tx, tz), -limx), limx);
+    const float cy = fminf(fmaxf(fdiv(ty, tz), -limy), limy);
+    const float tz2 = fmul(tz, tz);
+    const float J00 = fdiv(focal_x, tz);
+    const float J02 = fdiv(fmul(fmul(tz, -cx), focal_x), tz2);
+    const float J11 = fdiv(focal_y, tz);
+    const float J12 = fdiv(fmul(fmul(tz, -cy), focal_y), tz2);
+    // T = W * J, rows r of W^T: W[0][r]=v[4r], W[1][r]=v[4r+1], W[2][r]=v[4r+2]
+    float T0[3], T1[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        T0[r] = ffma(v[4 * r + 2], J02, fmul(v[4 * r], J00));
+        T1[r] = ffma(v[4 * r + 2], J12, fmul(v[4 * r + 1], J11));
+    }
+    // X = T^T * Vrk^T ; cov = X * T
+    const float B0[3] = {cov3D[0], cov3D[1], cov3D[2]};
+    const float B1[3] = {cov3D[1], cov3D[3], cov3D[4]};
+    const float B2[3] = {cov3D[2], cov3D[4], cov3D[5]};
+    const float X00 = dot3(T0[0], B0[0], T0[1], B0[1], T0[2], B0[2]);
+    const float X10 = dot3(T0[0], B1[0], T0[1], B1[1], T0[2], B1[2]);
+    const float X20 = dot3(T0[0], B2[0], T0[1], B2[1], T0[2], B2[2]);
+    const float X01 = dot3(T1[0], B0[0], T1[1], B0[1], T1[2], B0[2]);
+    const float X11 = dot3(T1[0], B1[0], T1[1], B1[1], T1[2], B1[2]);
+    const float X21 = dot3(T1[0], B2[0], T1[1], B2[1], T1[2], B2[2]);
+    const float a = fadd(dot3(X00, T0[0], X10, T0[1], X20, T0[2]), 0.3f);
+    const float b = dot3(X01, T0[0], X11, T0[1], X21, T0[2]);
+    const float c = fadd(dot3(X01, T1[0], X11, T1[1], X21, T1[2]), 0.3f);
+    o.a = a; o.b = b; o.c = c;
+
+    const float det = ffma(a, c, -fmul(b, b));
+    if (det == 0.0f) return;  // forward.cu:219-221
+    const float det_inv = frcp(det);
+    o.conx = fmul(c, det_inv);
+    o.cony = fmul(b, -det_inv);
+    o.conz = fmul(a, det_inv);
+
+    const float mid = fmul(fadd(a, c), 0.5f);
+    const float s = fsqrt(fmaxf(ffma(mid, mid, -det), 0.1f));
+    const float lam = fmaxf(fadd(mid, s), fadd(mid, -s));
+    const int radius = __float2int_ru(fmul(fsqrt(lam), 3.0f));
+
+    // ndc2Pix is evaluated in double in the reference (auxiliary.h:41-44)
+    const float px = (float)__dmul_rn(__fma_rn(__dadd_rn((double)ndc_x, 1.0), (double)W, -1.0), 0.5);
+    const float py = (float)__dmul_rn(__fma_rn(__dadd_rn((double)ndc_y, 1.0), (double)H, -1.0), 0.5);
+    o.px = px; o.py = py;
+
+    // getRect, auxiliary.h:46-56
+    const float rf = (float)radius;
+    const int ix0 = __float2int_rz(fmul(fadd(px, -rf), 0.0625f));
+    const int iy0 = __float2int_rz(fmul(fadd(py, -rf), 0.0625f));
+    const int ix1 = __float2int_rz(fmul(fadd(fadd(fadd(px, rf), 16.0f), -1.0f), 0.0625f));
+    const int iy1 = __float2int_rz(fmul(fadd(fadd(fadd(py, rf), 16.0f), -1.0f), 0.0625f));
+    o.xmin = min(grid_x, (uint32_t)max(0, ix0));
+    o.ymin = min(grid_y, (uint32_t)max(0, iy0));
+    o.xmax = min(grid_x, (uint32_t)max(0, ix1));
+    o.ymax = min(grid_y, (uint32_t)max(0, iy1));
+    if ((o.xmax - o.xmin) * (o.ymax - o.ymin) == 0) return;  // forward.cu:236
+    o.radius = radius;
+    o.visible = true;
+}
+
+// SH -> RGB, forward.cu:20-71.  Returns the clamp mask in bits 0..2.
+__device__ __forceinline__ uint32_t sh_to_rgb(int deg, const float* __restrict__ sh /* [M][3] of this Gaussian */,
+                                              float px, float py, float pz, const float* __restrict__ campos,
+                                              float* rgb) {
+    const float dx = fadd(-campos[0], px), dy = fadd(-campos[1], py), dz = fadd(-campos[2], pz);
+    const float len = fsqrt(ffma(dz, dz, ffma(dx, dx, fmul(dy, dy))));
+    const float x = fdiv(dx, len), y = fdiv(dy, len), z = fdiv(dz, len);
+    float res[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) res[ch] = fmul(sh[ch], 0.28209479177387814f);
+    if (deg > 0) {
+        const float c1y = fmul(y, 0.4886025119029199f), c1z = fmul(z, 0.4886025119029199f),
+                    c1x = fmul(x, 0.4886025119029199f);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float r = ffma(-c1y, sh[3 + ch], res[ch]);
+            r = ffma(c1z, sh[6 + ch], r);
+            res[ch] = ffma(-c1x, sh[9 + ch], r);
+        }
+        if (deg > 1) {
+            const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
+            const float xy = fmul(y, x), yz = fmul(z, y), xz = fmul(z, x);
+            const float k4 = fmul(xy, 1.0925484305920792f);
+            const float k5 = fmul(yz, -1.0925484305920792f);
+            const float zz2 = fadd(zz, zz);
+            const float k6 = fmul(fadd(-yy, fadd(-xx, zz2)), 0.31539156525252005f);
+            const float k7 = fmul(xz, -1.0925484305920792f);
+            const float xx_yy = fadd(xx, -yy);
+            const float k8 = fmul(xx_yy, 0.5462742152960396f);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float r = ffma(k4, sh[12 + ch], res[ch]);
+                r = ffma(k5, sh[15 + ch], r);
+                r = ffma(k6, sh[18 + ch], r);
+                r = ffma(k7, sh[21 + ch], r);
+                res[ch] = ffma(k8, sh[24 + ch], r);
+            }
+            if (deg > 2) {
+                const float k9 = fmul(fmul(y, -0.5900435899266435f), ffma(xx, 3.0f, -yy));
+                const float k10 = fmul(fmul(xy, 2.890611442640554f), z);
+                const float f4 = fadd(-yy, ffma(zz, 4.0f, -xx));  // 4zz - xx - yy
+                const float k11 = fmul(fmul(y, -0.4570457994644658f), f4);
+                const float k12 = fmul(fmul(z, 0.3731763325901154f), ffma(yy, -3.0f, ffma(xx, -3.0f, zz2)));
+                const float k13 = fmul(f4, fmul(x, -0.4570457994644658f));
+                const float k14 = fmul(xx_yy, fmul(z, 1.445305721320277f));
+                const float k15 = fmul(fmul(x, -0.5900435899266435f), ffma(yy, -3.0f, xx));
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    float r = ffma(k9, sh[27 + ch], res[ch]);
+                    r = ffma(k10, sh[30 + ch], r);
+                    r = ffma(k11, sh[33 + ch], r);
+                    r = ffma(k12, sh[36 + ch], r);
+                    r = ffma(k13, sh[39 + ch], r);
+                    r = ffma(k14, sh[42 + ch], r);
+                    res[ch] = ffma(k15, sh[45 + ch], r);
+                }
+            }
+        }
+    }
+    uint32_t clamp_mask = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float r = fadd(res[ch], 0.5f);
+        if (r < 0.0f) clamp_mask |= 1u << ch;
+        rgb[ch] = r < 0.0f ? 0.0f : r;
+    }
+    return clamp_mask;
+}
+
+// Conservative half extents of {pixels that can reach alpha >= 1/255} for the *stored*
+// conic/opacity (the quantities the blend evaluates).  Used only to skip work whose result
+// the reference would discard (forward.cu:418-426), never to change a result.
+__device__ __forceinline__ void alpha_footprint(float A, float B, float C, float opacity, int radius, float& hx,
+                                                float& hy) {
+    const float inf = __int_as_float(0x7f800000);
+    hx = inf; hy = inf;
+    if (!(opacity >= 0.0f) || !isfinite(A) || !isfinite(B) || !isfinite(C)) return;  // keep exact behaviour for odd inputs
+    if (opacity < 1.0f / 255.0f) { hx = -inf; hy = -inf; return; }  // alpha = o*G <= o < 1/255 always
+    const double dA = A, dB = B, dC = C;
+    const double D = dA * dC - dB * dB;
+    if (!(D > 0.0) || !(dA > 0.0) || !(dC > 0.0)) return;  // not an ellipse: no culling
+    // alpha >= 1/255  <=>  A dx^2 + 2B dx dy + C dy^2 <= 2 ln(255 o) =: tau
+    double tau = 2.0 * log(255.0 * (double)opacity);
+    // slack for the float evaluation of `power` (three products, two sums) at |d| <= radius + 16
+    const double dmax = (double)radius + 17.0;
+    tau += 8.0 * 1.1920929e-7 * (fabs(dA) + fabs(dC) + 2.0 * fabs(dB)) * dmax * dmax + 1e-4;
+    tau *= 1.0 + 1e-5;
+    if (tau <= 0.0) { hx = -inf; hy = -inf; return; }
+    const double ex = sqrt(tau * dC / D) + 1e-2;
+    const double ey = sqrt(tau * dA / D) + 1e-2;
+    hx = __double2float_ru(ex);
+    hy = __double2float_ru(ey);
+}
+
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(
+    int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
+    const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
+    const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
+    const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
+    int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
+    int prefiltered, int* __restrict__ radii, Rec* __restrict__ rec, uint32_t* __restrict__ depth_key,
+    uint2* __restrict__ rect, uint32_t* __restrict__ tiles_touched, float* __restrict__ cov3D_out,
+    uint8_t* __restrict__ clamped) {
+    __shared__ float s_cam[35];
+    if (threadIdx.x < 16) s_cam[threadIdx.x] = viewmatrix[threadIdx.x];
+    else if (threadIdx.x < 32) s_cam[threadIdx.x] = projmatrix[threadIdx.x - 16];
+    else if (threadIdx.x < 35) s_cam[threadIdx.x] = cam_pos[threadIdx.x - 32];
+    __syncthreads();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float* v = s_cam;
+    const float* m = s_cam + 16;
+
+    const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    float cov3D[6];
+    ProjOut o;
+    // cheap early cull before touching the other attribute arrays
+    const float tz = xform_row(v, 2, x, y, z);
+    bool vis = !(tz <= 0.2f);
+    if (!vis && prefiltered) {
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+    }
+    if (vis) {
+        if (cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cov3D[k] = cov3D_precomp[6 * (size_t)idx + k];
+        } else {
+            const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+            cov3d_from_scale_rot(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2], scale_modifier, q.x, q.y,
+                                 q.z, q.w, cov3D);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cov3D_out[6 * (size_t)idx + k] = cov3D[k];
+        }
+        project_gaussian(x, y, z, v, m, cov3D, W, H, tan_fovx, tan_fovy, focal_x, focal_y, grid_x, grid_y, o);
+        vis = o.visible;
+    }
+    if (!vis) {
+        radii[idx] = 0;
+        tiles_touched[idx] = 0;
+        depth_key[idx] = 0xFFFFFFFFu;
+        rect[idx] = make_uint2(0u, 0u);
+        return;
+    }
+    float rgb[3];
+    uint32_t cmask = 0;
+    if (colors_precomp != nullptr) {
+        rgb[0] = colors_precomp[3 * idx]; rgb[1] = colors_precomp[3 * idx + 1]; rgb[2] = colors_precomp[3 * idx + 2];
+    } else {
+        cmask = sh_to_rgb(D, shs + (size_t)idx * M * 3, x, y, z, s_cam + 32, rgb);
+        clamped[idx] = (uint8_t)cmask;
+    }
+    const float opacity = opacities[idx];
+    float hx, hy;
+    alpha_footprint(o.conx, o.cony, o.conz, opacity, o.radius, hx, hy);
+    Rec r;
+    r.a = make_float4(o.px, o.py, hx, hy);
+    r.b = make_float4(o.conx, o.cony, o.conz, opacity);
+    r.c = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
+    rec[idx] = r;
+    radii[idx] = o.radius;
+    tiles_touched[idx] = (o.xmax - o.xmin) * (o.ymax - o.ymin);
+    depth_key[idx] = __float_as_uint(o.depth);
+    rect[idx] = make_uint2(o.xmin | (o.xmax << 16), o.ymin | (o.ymax << 16));
+}
+
+// checkFrustum, rasterizer_impl.cu:54-66
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                                           const float* __restrict__ viewmatrix,
+                                                           uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float tz = xform_row(viewmatrix, 2, means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    present[idx] = !(tz <= 0.2f);
+}
+
+// filter_preprocessCUDA, forward.cu:259-334
+__global__ void __launch_bounds__(256) visible_filter_kernel(
+    int P, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
+    const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
+    const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, int W, int H, float tan_fovx,
+    float tan_fovy, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y, int* __restrict__ radii,
+    float* __restrict__ means2D) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    radii[idx] = 0;
+    const float tz = xform_row(viewmatrix, 2, x, y, z);
+    if (tz <= 0.2f) return;
+    float cov3D[6];
+    if (cov3D_precomp != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cov3D[k] = cov3D_precomp[6 * (size_t)idx + k];
+    } else {
+        const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+        cov3d_from_scale_rot(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2], scale_modifier, q.x, q.y, q.z,
+                             q.w, cov3D);
+    }
+    ProjOut o;
+    project_gaussian(x, y, z, viewmatrix, projmatrix, cov3D, W, H, tan_fovx, tan_fovy, focal_x, focal_y, grid_x,
+                     grid_y, o);
+    if (!o.visible) return;
+    radii[idx] = o.radius;
+    means2D[2 * idx] = o.px;
+    means2D[2 * idx + 1] = o.py;
+}
+
+void launch_preprocess_fwd(const grpg_forward_args* a, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
+                           Rec* rec, uint32_t* depth_key, uint2* rect, uint32_t* tiles_touched, float* cov3d,
+                           uint8_t* clamped, cudaStream_t stream) {
+    const int P = a->P;
+    preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+        P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs, a->cov3D_precomp,
+        a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos, a->width, a->height, a->tan_fovx, a->tan_fovy,
+        focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped);
+}
+
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream) {
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+}
+
+void launch_visible_filter(int P, int W, int H, const float* means3D, const float* scales, float scale_modifier,
+                           const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                           const float* projmatrix, float tan_fovx, float tan_fovy, int* radii, float* means2D,
+                           cudaStream_t stream) {
+    const float focal_y = H / (2.0f * tan_fovy), focal_x = W / (2.0f * tan_fovx);
+    const uint32_t gx = (W + 15) / 16, gy = (H + 15) / 16;
+    visible_filter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, scales, scale_modifier, rotations,
+                                                               cov3D_precomp, viewmatrix, projmatrix, W, H, tan_fovx,
+                                                               tan_fovy, focal_x, focal_y, gx, gy, radii, means2D);
+}
+
+}  // namespace grpg

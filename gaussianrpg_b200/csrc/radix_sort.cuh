@@ -1,0 +1,239 @@
+// radix_sort.cuh -- hand-written onesweep LSD radix sort of (uint32 key, uint32 value) pairs.
+//
+// Replaces cub::DeviceRadixSort::SortPairs as used at rasterizer_impl.cu:306-311 of the
+// reference.  One kernel per digit pass; each CTA ranks a 4096-key tile with warp-level
+// match/ballot multi-split (stable), publishes its per-digit counts and resolves its global
+// offsets by decoupled look-back over the preceding tiles (single read + single write of the
+// data per pass).  A separate histogram kernel reads the keys once for all passes.
+//
+// HBM traffic per pass: 8 B read + 8 B written per pair (+ 4 B per pair once for the
+// histogram); look-back state is 1 KB per tile and lives in L2.
+#pragma once
+#include "grpg_common.cuh"
+
+namespace grpg {
+
+constexpr uint32_t LB_FLAG_AGG = 1u << 30;
+constexpr uint32_t LB_FLAG_PREFIX = 2u << 30;
+constexpr uint32_t LB_FLAG_MASK = 3u << 30;
+constexpr uint32_t LB_VALUE_MASK = ~LB_FLAG_MASK;
+
+struct SortPlan {
+    int passes;
+    int bits[SORT_MAX_PASSES];
+    int shift[SORT_MAX_PASSES];
+};
+
+static inline SortPlan make_sort_plan(int total_bits) {
+    SortPlan p{};
+    if (total_bits < 1) total_bits = 1;
+    p.passes = (total_bits + 7) / 8;
+    int per = (total_bits + p.passes - 1) / p.passes;
+    int s = 0;
+    for (int i = 0; i < p.passes; ++i) {
+        int b = per;
+        if (s + b > total_bits) b = total_bits - s;
+        p.bits[i] = b;
+        p.shift[i] = s;
+        s += b;
+    }
+    return p;
+}
+
+// ---- histogram of every pass' digit in one read ---------------------------------------
+__global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+                                                             SortPlan plan, uint32_t* __restrict__ hist /*[passes][256]*/) {
+    __shared__ uint32_t s_hist[SORT_MAX_PASSES][256];
+    for (int i = threadIdx.x; i < SORT_MAX_PASSES * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x * 4;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * 4; base < n; base += stride) {
+        uint32_t k[4];
+        int cnt = 4;
+        if (base + 4 <= n) {
+            uint4 v = *reinterpret_cast<const uint4*>(keys + base);
+            k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+        } else {
+            cnt = n - base;
+            for (int j = 0; j < cnt; ++j) k[j] = keys[base + j];
+        }
+        for (int j = 0; j < cnt; ++j) {
+#pragma unroll
+            for (int p = 0; p < SORT_MAX_PASSES; ++p)
+                if (p < plan.passes) atomicAdd(&s_hist[p][(k[j] >> plan.shift[p]) & ((1u << plan.bits[p]) - 1)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.passes * 256; i += blockDim.x) {
+        uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// exclusive scan of one value per thread across a 256-thread block
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp /*[8]*/, uint32_t* total = nullptr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        uint32_t c = s_warp[w];
+        if (w < warp) wbase += c;
+        tot += c;
+    }
+    if (total) *total = tot;
+    __syncthreads();
+    return wbase + inc - v;
+}
+
+// ---- one onesweep digit pass -----------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift, int bits,
+    const uint32_t* __restrict__ hist /*[256] for this pass*/, uint32_t* __restrict__ tile_counter,
+    uint32_t* __restrict__ lookback /*[tiles][256]*/) {
+    __shared__ uint32_t s_warp_hist[8][256];
+    __shared__ uint32_t s_local_start[256];
+    __shared__ uint32_t s_bin_base[256];
+    __shared__ uint32_t s_keys[SORT_TILE];
+    __shared__ uint32_t s_vals[SORT_TILE];
+    __shared__ uint32_t s_scan[8];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t mask = (1u << bits) - 1u;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s_warp_hist[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t tile_base = tile * SORT_TILE;
+    const uint32_t warp_base = tile_base + warp * (32 * SORT_IPT);
+
+    uint32_t key[SORT_IPT];
+    uint16_t rank[SORT_IPT];
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; ++i) {
+        uint32_t idx = warp_base + i * 32 + lane;
+        key[i] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
+    }
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; ++i) {
+        uint32_t d = (key[i] >> shift) & mask;
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t pre = s_warp_hist[warp][d];
+        __syncwarp();
+        if ((peers & lt_mask) == 0) s_warp_hist[warp][d] = pre + __popc(peers);
+        __syncwarp();
+        rank[i] = (uint16_t)(pre + __popc(peers & lt_mask));
+    }
+    __syncthreads();
+
+    // per-digit: exclusive offsets of each warp inside the digit, tile total
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        uint32_t c = s_warp_hist[w][tid];
+        s_warp_hist[w][tid] = total;
+        total += c;
+    }
+    // publish the tile aggregate as early as possible
+    uint32_t* my_lb = lookback + (size_t)tile * 256 + tid;
+    st_volatile_u32(my_lb, total | (tile == 0 ? LB_FLAG_PREFIX : LB_FLAG_AGG));
+
+    uint32_t local_start = block_exclusive_scan_256(total, s_scan);
+    uint32_t ghist = hist[tid];
+    uint32_t gexcl = block_exclusive_scan_256(ghist, s_scan);
+
+    // decoupled look-back over preceding tiles for digit `tid`
+    uint32_t excl = 0;
+    if (tile > 0) {
+        int t = (int)tile - 1;
+        while (true) {
+            uint32_t v = ld_volatile_u32(lookback + (size_t)t * 256 + tid);
+            uint32_t f = v & LB_FLAG_MASK;
+            if (f == 0) continue;  // not published yet
+            excl += v & LB_VALUE_MASK;
+            if (f == LB_FLAG_PREFIX) break;
+            --t;  // t >= 0 always terminates at tile 0, which publishes PREFIX
+        }
+        st_volatile_u32(my_lb, (excl + total) | LB_FLAG_PREFIX);
+    }
+    s_local_start[tid] = local_start;
+    s_bin_base[tid] = gexcl + excl - local_start;
+    __syncthreads();
+
+    // scatter keys and values into tile-sorted order in shared memory
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; ++i) {
+        uint32_t idx = warp_base + i * 32 + lane;
+        uint32_t d = (key[i] >> shift) & mask;
+        uint32_t p = s_local_start[d] + s_warp_hist[warp][d] + rank[i];
+        s_keys[p] = key[i];
+        s_vals[p] = idx < n ? vals_in[idx] : 0u;
+    }
+    __syncthreads();
+    // coalesced-by-run write-out: slot p of the tile goes to s_bin_base[digit] + p
+    const uint32_t valid = (n - tile_base) < (uint32_t)SORT_TILE ? (n - tile_base) : (uint32_t)SORT_TILE;
+#pragma unroll
+    for (int k = 0; k < SORT_IPT; ++k) {
+        uint32_t p = k * SORT_THREADS + tid;
+        if (p < valid) {
+            uint32_t kk = s_keys[p];
+            uint32_t o = s_bin_base[(kk >> shift) & mask] + p;
+            keys_out[o] = kk;
+            vals_out[o] = s_vals[p];
+        }
+    }
+}
+
+// Sorts n pairs on bits [0, total_bits).  Input in (keys_a, vals_a); (keys_b, vals_b) is the
+// ping-pong partner.  Returns true when the sorted result ends in the *_a buffers, false for *_b.
+// `aux` must hold SORT_MAX_PASSES*(256+64) uint32 + SORT_MAX_PASSES*tiles*256 uint32 and is
+// cleared here.
+static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                                       long long n, int total_bits, uint32_t* aux, int num_sms, cudaStream_t stream) {
+    if (n <= 0) return true;
+    SortPlan plan = make_sort_plan(total_bits);
+    size_t tiles = sort_num_tiles(n);
+    uint32_t* hist = aux;                                  // [4][256]
+    uint32_t* counters = aux + SORT_MAX_PASSES * 256;      // [4] (padded to 64 words)
+    uint32_t* lookback = aux + SORT_MAX_PASSES * (256 + 64);
+    size_t clear_words = (size_t)SORT_MAX_PASSES * (256 + 64) + (size_t)plan.passes * tiles * 256;
+    cudaMemsetAsync(aux, 0, clear_words * sizeof(uint32_t), stream);
+    int hgrid = (int)((n + 256 * 4 * 8 - 1) / (256 * 4 * 8));
+    if (hgrid > num_sms * 8) hgrid = num_sms * 8;
+    if (hgrid < 1) hgrid = 1;
+    sort_histogram_kernel<<<hgrid, 256, 0, stream>>>(keys_a, (uint32_t)n, plan, hist);
+    bool in_a = true;
+    for (int p = 0; p < plan.passes; ++p) {
+        const uint32_t* ki = in_a ? keys_a : keys_b;
+        const uint32_t* vi = in_a ? vals_a : vals_b;
+        uint32_t* ko = in_a ? keys_b : keys_a;
+        uint32_t* vo = in_a ? vals_b : vals_a;
+        onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
+            ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p,
+            lookback + (size_t)p * tiles * 256);
+        in_a = !in_a;
+    }
+    return in_a;
+}
+
+}  // namespace grpg

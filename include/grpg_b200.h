@@ -1,0 +1,200 @@
+/*
+ * grpg_b200.h -- C-ABI of the B200-native differentiable 3D-Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of GimpelZhang/GaussianRPG's
+ * `diff_gaussian_rasterization` extension.  Every entry point takes plain device
+ * pointers, sizes and a cudaStream_t (as void*); no torch type crosses the ABI.
+ * Each function cites the reference interface it replaces (paths relative to
+ * submodules/diff-gaussian-rasterization/ of the reference).
+ *
+ * Return value: 0 on success, non-zero on error; grpg_last_error() returns a
+ * thread-local, NUL-terminated description of the most recent failure.
+ *
+ * All device buffers are owned by the caller (the Python binding allocates them
+ * as torch tensors, exactly as rasterize_points.cu:70-83 does in the reference).
+ * The three workspaces (geometry / binning / image) are opaque byte blobs whose
+ * size is obtained from the grpg_*_workspace_bytes() queries; their internal
+ * layout is private, but grpg_*_layout() exposes the sub-array offsets that the
+ * parity tests need (radii, tiles_touched, point_list, ranges, n_contrib).
+ */
+#ifndef GRPG_B200_H_
+#define GRPG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRPG_NUM_CHANNELS 3   /* cuda_rasterizer/config.h:15 */
+#define GRPG_BLOCK_X 16       /* cuda_rasterizer/config.h:17 */
+#define GRPG_BLOCK_Y 16       /* cuda_rasterizer/config.h:18 */
+#define GRPG_MAX_SEMANTIC_BWD 32 /* reference: NUM_CLASSES 20 (config.h:16); we lift it to 32 and raise beyond */
+
+/* ------------------------------------------------------------------------- */
+/* Workspace layout (private, exposed for the parity tests only).            */
+/* ------------------------------------------------------------------------- */
+typedef struct grpg_geom_layout {
+    size_t total_bytes;
+    size_t rec;            /* float4[3*P]: (x,y,hx,hy) (A,B,C,opacity) (r,g,b,depth)        */
+    size_t depth_key;      /* uint32[P]: float bits of view depth, 0xFFFFFFFF if culled     */
+    size_t rect;           /* uint32[2*P]: xmin | xmax<<16, ymin | ymax<<16                 */
+    size_t tiles_touched;  /* uint32[P]                                                     */
+    size_t cov3d;          /* float[6*P]                                                    */
+    size_t clamped;        /* uint8[P]: bit c set when SH colour channel c was clamped      */
+    size_t sorted_idx;     /* uint32[P]: Gaussian ids ordered by (depth bits, id)           */
+    size_t offsets;        /* uint32[P]: exclusive scan of tiles_touched in sorted order    */
+    size_t scratch;        /* sort ping-pong buffers, histograms, look-back state           */
+    size_t num_rendered;   /* uint32[1] device copy of R                                    */
+} grpg_geom_layout;
+
+typedef struct grpg_binning_layout {
+    size_t total_bytes;
+    size_t point_list;     /* uint32[R]: Gaussian id per instance, sorted by (tile, depth, id) */
+    size_t tile_keys;      /* uint32[R]: tile id per sorted instance                           */
+    size_t scratch;        /* ping-pong + look-back                                            */
+} grpg_binning_layout;
+
+typedef struct grpg_image_layout {
+    size_t total_bytes;
+    size_t n_contrib;      /* uint32[W*H]  */
+    size_t ranges;         /* uint2[tiles] */
+} grpg_image_layout;
+
+/* replaces required<GeometryState>(P)  (cuda_rasterizer/rasterizer_impl.h:62-72, rasterizer_impl.cu:155-170) */
+int grpg_get_geometry_layout(int P, grpg_geom_layout* out);
+/* replaces required<BinningState>(R)   (rasterizer_impl.cu:181-193) */
+int grpg_get_binning_layout(long long num_rendered, grpg_binning_layout* out);
+/* replaces required<ImageState>(W*H)   (rasterizer_impl.cu:172-179) */
+int grpg_get_image_layout(int width, int height, grpg_image_layout* out);
+
+/* ------------------------------------------------------------------------- */
+/* Forward.  Replaces CudaRasterizer::Rasterizer::forward                     */
+/* (cuda_rasterizer/rasterizer.h:33-64, rasterizer_impl.cu:197-343) as bound  */
+/* by RasterizeGaussiansCUDA (rasterize_points.cu:35-124).                    */
+/* It is split in two calls because the binning workspace is sized by the     */
+/* instance count R, which the caller must allocate (the reference does the   */
+/* same through its resize callback after a blocking D2H copy,                */
+/* rasterizer_impl.cu:283-288).                                               */
+/* ------------------------------------------------------------------------- */
+typedef struct grpg_forward_args {
+    int P;              /* number of Gaussians                                            */
+    int D;              /* active SH degree               (raster_settings.sh_degree)     */
+    int M;              /* SH coefficients per Gaussian   (sh.size(1), 0 if no SH)        */
+    int S;              /* semantic channels              (semantics.size(1))             */
+    int width, height;
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int prefiltered;
+    int debug;
+    const float* background;     /* [3]      device */
+    const float* means3D;        /* [P,3]    device */
+    const float* shs;            /* [P,M,3]  device or NULL */
+    const float* colors_precomp; /* [P,3]    device or NULL */
+    const float* semantics;      /* [P,S]    device or NULL when S==0 */
+    const float* opacities;      /* [P,1]    device */
+    const float* scales;         /* [P,3]    device or NULL */
+    const float* rotations;      /* [P,4]    device or NULL */
+    const float* cov3D_precomp;  /* [P,6]    device or NULL */
+    const float* viewmatrix;     /* [16]     device, column-major-in-memory as the caller passes it */
+    const float* projmatrix;     /* [16]     device */
+    const float* cam_pos;        /* [3]      device */
+    float* out_color;            /* [3,H,W]  device */
+    float* out_depth;            /* [1,H,W]  device */
+    float* out_alpha;            /* [1,H,W]  device */
+    float* out_semantic;         /* [S,H,W]  device or NULL */
+    int*   radii;                /* [P]      device */
+    void*  geom_ws;              /* grpg_geom_layout.total_bytes    */
+    void*  binning_ws;           /* grpg_binning_layout.total_bytes (stage 2 only) */
+    void*  image_ws;             /* grpg_image_layout.total_bytes   */
+    void*  stream;               /* cudaStream_t */
+} grpg_forward_args;
+
+/* Stage 1: projection (preprocessCUDA forward.cu:155-256), depth ordering and the
+ * prefix sum of tile counts (rasterizer_impl.cu:280).  Writes R to *num_rendered
+ * (host) after synchronising `stream` -- the one host sync of the forward path
+ * (reference: rasterizer_impl.cu:284). */
+int grpg_forward_geometry(const grpg_forward_args* a, int* num_rendered);
+
+/* Stage 2: instance emission (duplicateWithKeys rasterizer_impl.cu:70-111), the
+ * (tile | depth | id) ordering (SortPairs rasterizer_impl.cu:306-311), tile ranges
+ * (identifyTileRanges :116-138) and the per-tile front-to-back blend (renderCUDA
+ * forward.cu:340-467). */
+int grpg_forward_render(const grpg_forward_args* a, int num_rendered);
+
+/* ------------------------------------------------------------------------- */
+/* Backward.  Replaces CudaRasterizer::Rasterizer::backward                   */
+/* (rasterizer.h:85-115, rasterizer_impl.cu:396-506) as bound by              */
+/* RasterizeGaussiansBackwardCUDA (rasterize_points.cu:126-220).              */
+/* All dL_* outputs are fully written by the call (no pre-zeroing needed).    */
+/* ------------------------------------------------------------------------- */
+typedef struct grpg_backward_args {
+    int P, D, M, S, R;
+    int width, height;
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int debug;
+    const float* background;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* semantics;
+    const float* alphas;          /* out_alpha of the forward [1,H,W] */
+    const float* scales;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* cam_pos;
+    const int*   radii;
+    const void*  geom_ws;
+    const void*  binning_ws;
+    const void*  image_ws;
+    const float* dL_dpix;         /* [3,H,W] */
+    const float* dL_dpix_depth;   /* [1,H,W] */
+    const float* dL_dalphas;      /* [1,H,W] */
+    const float* dL_dpix_semantic;/* [S,H,W] or NULL */
+    float* dL_dmean2D;            /* [P,3]  (x, y in NDC units, |x|+|y|)  backward.cu:625-628 */
+    float* dL_dconic;             /* [P,4]  (.z unused, written 0)        backward.cu:633-635 */
+    float* dL_dopacity;           /* [P,1] */
+    float* dL_dcolor;             /* [P,3] */
+    float* dL_ddepth;             /* [P,1] */
+    float* dL_dmean3D;            /* [P,3] */
+    float* dL_dcov3D;             /* [P,6] */
+    float* dL_dsh;                /* [P,M,3] or NULL when M==0 */
+    float* dL_dscale;             /* [P,3] */
+    float* dL_drot;               /* [P,4] */
+    float* dL_dsemantic;          /* [P,S] or NULL when S==0 */
+    void*  grad_ws;               /* grpg_backward_workspace_bytes(P,S) scratch */
+    void*  stream;
+} grpg_backward_args;
+
+size_t grpg_backward_workspace_bytes(int P, int S);
+int grpg_backward(const grpg_backward_args* a);
+
+/* replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:25-31, rasterizer_impl.cu:141-153) */
+int grpg_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                      const float* projmatrix, uint8_t* present, void* stream);
+
+/* replaces CudaRasterizer::Rasterizer::visible_filter (rasterizer.h:66-83, rasterizer_impl.cu:345-392) */
+int grpg_visible_filter(int P, int width, int height,
+                        const float* means3D, const float* scales, float scale_modifier,
+                        const float* rotations, const float* cov3D_precomp,
+                        const float* viewmatrix, const float* projmatrix,
+                        float tan_fovx, float tan_fovy,
+                        int* radii, float* means2D, void* stream);
+
+/* Reconstructs the reference's sorted 64-bit keys ((tile << 32) | depth bits,
+ * rasterizer_impl.cu:102-104) from our workspaces -- test hook for the bit-exact
+ * key comparison. */
+int grpg_debug_reference_keys(int P, long long num_rendered, const void* geom_ws,
+                              const void* binning_ws, uint64_t* keys_out, void* stream);
+
+const char* grpg_last_error(void);
+int grpg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRPG_B200_H_ */
