@@ -37,6 +37,30 @@ void launch_preprocess_bwd(const grpg_backward_args* a, const float* cov3D, cons
 
 using namespace grpg;
 
+// ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------
+#include <map>
+#include <vector>
+namespace {
+struct ProfEntry { std::string name; cudaEvent_t e0, e1; };
+bool g_prof_on = false;
+std::vector<ProfEntry> g_prof;
+}  // namespace
+namespace grpg {
+void prof_range_begin(const char* name, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    ProfEntry e;
+    e.name = name;
+    cudaEventCreate(&e.e0);
+    cudaEventCreate(&e.e1);
+    cudaEventRecord(e.e0, stream);
+    g_prof.push_back(e);
+}
+void prof_range_end(cudaStream_t stream) {
+    if (!g_prof_on || g_prof.empty()) return;
+    cudaEventRecord(g_prof.back().e1, stream);
+}
+}  // namespace grpg
+
 static thread_local std::string g_last_error;
 static int fail(const std::string& msg) {
     g_last_error = msg;
@@ -68,6 +92,42 @@ static unsigned long long* pinned_word() {
 extern "C" {
 
 const char* grpg_last_error(void) { return g_last_error.c_str(); }
+
+int grpg_profile_begin(void) {
+    for (auto& e : g_prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+    g_prof.clear();
+    g_prof_on = true;
+    return 0;
+}
+
+// Writes "name:count:total_ms\n" lines into buf; returns the number of distinct kernels.
+int grpg_profile_end(char* buf, size_t buf_len) {
+    g_prof_on = false;
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<int, double>> acc;
+    std::vector<std::string> order;
+    for (auto& e : g_prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.e0, e.e1);
+        if (!acc.count(e.name)) order.push_back(e.name);
+        acc[e.name].first += 1;
+        acc[e.name].second += ms;
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+    }
+    g_prof.clear();
+    std::string out;
+    for (auto& n : order) {
+        char line[256];
+        snprintf(line, sizeof line, "%s:%d:%.6f\n", n.c_str(), acc[n].first, acc[n].second);
+        out += line;
+    }
+    if (buf && buf_len) {
+        strncpy(buf, out.c_str(), buf_len - 1);
+        buf[buf_len - 1] = 0;
+    }
+    return (int)order.size();
+}
 int grpg_version(void) { return 100; }
 
 int grpg_get_geometry_layout(int P, grpg_geom_layout* out) {

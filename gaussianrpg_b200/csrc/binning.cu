@@ -190,13 +190,18 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
     p += align_up((scan_tiles + 2) * 8, 256);
     uint32_t* scan_counter = (uint32_t*)p;
 
-    iota_kernel<<<(P + 255) / 256, 256, 0, stream>>>(sorted_idx, (uint32_t)P);
-    bool in_a = onesweep_sort_pairs(depth_key, sorted_idx, keys_b, vals_b, P, 32, aux, num_sms, stream);
+    {
+        ProfScope ps("iota", stream);
+        iota_kernel<<<(P + 255) / 256, 256, 0, stream>>>(sorted_idx, (uint32_t)P);
+    }
+    bool in_a = onesweep_sort_pairs(depth_key, sorted_idx, keys_b, vals_b, P, 32, aux, num_sms, stream,
+                                    "depth_sort_hist", "depth_sort_pass");
     if (!in_a) {  // 32 bits -> 4 passes -> always lands back in the a-buffers; kept for safety
         cudaMemcpyAsync(depth_key, keys_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(sorted_idx, vals_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
     }
     cudaMemsetAsync(status, 0, (scan_tiles + 2) * 8 + 256, stream);
+    ProfScope ps("scan_tiles", stream);
     scan_tiles_kernel<<<(unsigned)scan_tiles, 256, 0, stream>>>(sorted_idx, tiles_touched, (uint32_t)P, offsets, status,
                                                                  scan_counter, num_rendered_dev);
 }
@@ -220,8 +225,12 @@ void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tile
     uint32_t* v0 = start_in_final ? point_list : vals_b;
     uint32_t* k1 = start_in_final ? keys_b : tile_keys;
     uint32_t* v1 = start_in_final ? vals_b : point_list;
-    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(sorted_idx, offsets, rect, (uint32_t)P, grid_x, k0, v0);
-    onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream);
+    {
+        ProfScope ps("emit_instances", stream);
+        emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(sorted_idx, offsets, rect, (uint32_t)P, grid_x, k0, v0);
+    }
+    onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream, "tile_sort_hist", "tile_sort_pass");
+    ProfScope ps("tile_ranges", stream);
     tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(tile_keys, (uint32_t)R, ranges);
 }
 

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                 const int pos = top - 1 - k;  // 0-based position in the tile's range
                 const float4 a = s_a[k];
                 const float4 b = s_b[k];
+                const uint32_t gid = s_id[k];
                 const float dx = a.x - pxf, dy = a.y - pyf;
                 const float power = ffma(ffma(dx, fmul(dx, b.x), fmul(dy, fmul(dy, b.z))), -0.5f, -fmul(dy, fmul(dx, b.y)));
                 const float G = expf(power);
@@ -126,8 +127,15 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                 float g_sem[SB > 0 ? SB : 1];
 #pragma unroll
                 for (int i = 0; i < (SB > 0 ? SB : 1); ++i) g_sem[i] = 0.f;
+                // all loads happen before the divergent section
+                const float4 c = s_c[k];
+                float sv[SB > 0 ? SB : 1];
+                if (SB > 0) {
+                    const float* sp = semantics + (size_t)gid * S;
+#pragma unroll
+                    for (int i = 0; i < SB; ++i) sv[i] = i < S ? __ldg(sp + i) : 0.f;
+                }
                 if (active) {
-                    const float4 c = s_c[k];
                     T = T / (1.f - alpha);
                     const float w_at = alpha * T;
                     float dL_dopa = 0.f;
@@ -138,14 +146,12 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                     acc2 = last_alpha * lastc2 + (1.f - last_alpha) * acc2; lastc2 = c.z;
                     dL_dopa += (c.z - acc2) * dpix2; g_c2 = w_at * dpix2;
                     if (SB > 0) {
-                        const float* sp = semantics + (size_t)s_id[k] * S;
 #pragma unroll
                         for (int i = 0; i < SB; ++i) {
                             if (i < S) {
-                                const float sv = __ldg(sp + i);
                                 acc_sem[i] = last_alpha * last_sem[i] + (1.f - last_alpha) * acc_sem[i];
-                                last_sem[i] = sv;
-                                dL_dopa += (sv - acc_sem[i]) * dsem[i];
+                                last_sem[i] = sv[i];
+                                dL_dopa += (sv[i] - acc_sem[i]) * dsem[i];
                                 g_sem[i] = w_at * dsem[i];
                             }
                         }
@@ -183,7 +189,6 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                     case 6: mine = g_op; break;   case 7: mine = g_c0; break;  case 8: mine = g_c1; break;
                     case 9: mine = g_c2; break;   case 10: mine = g_d; break;  default: break;
                 }
-                const uint32_t gid = s_id[k];
                 if (lane < 11) atomicAdd(grad_rec + (size_t)gid * GREC + lane, mine);
                 if (SB > 0) {
 #pragma unroll
@@ -203,6 +208,7 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
                       const uint32_t* n_contrib, float* grad_rec, cudaStream_t stream) {
     const dim3 grid((a->width + GRPG_TILE - 1) / GRPG_TILE, (a->height + GRPG_TILE - 1) / GRPG_TILE, 1);
     const int S = a->S;
+    ProfScope ps("blend_bwd", stream);
 #define GRPG_BWD_LAUNCH(SBV)                                                                                      \
     blend_bwd_kernel<SBV><<<grid, 256, 0, stream>>>(ranges, point_list, rec, a->semantics, S, a->width, a->height,  \
                                                      a->background, a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth, \

@@ -282,6 +282,7 @@ void launch_preprocess_bwd(const grpg_backward_args* a, const float* cov3D, cons
     const int P = a->P;
     const float focal_y = a->height / (2.0f * a->tan_fovy);
     const float focal_x = a->width / (2.0f * a->tan_fovx);
+    ProfScope ps("preprocess_bwd", stream);
     preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, a->D, a->M, a->means3D, a->radii, a->shs, clamped, a->scales, a->rotations, a->scale_modifier, cov3D,
         a->viewmatrix, a->projmatrix, focal_x, focal_y, a->tan_fovx, a->tan_fovy, a->cam_pos, grad_rec, a->dL_dmean2D,

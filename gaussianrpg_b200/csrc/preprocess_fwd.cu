@@ -341,6 +341,7 @@ void launch_preprocess_fwd(const grpg_forward_args* a, float focal_x, float foca
                            Rec* rec, uint32_t* depth_key, uint2* rect, uint32_t* tiles_touched, float* cov3d,
                            uint8_t* clamped, cudaStream_t stream) {
     const int P = a->P;
+    ProfScope ps("preprocess_fwd", stream);
     preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs, a->cov3D_precomp,
         a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos, a->width, a->height, a->tan_fovx, a->tan_fovy,

@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 // `aux` must hold SORT_MAX_PASSES*(256+64) uint32 + SORT_MAX_PASSES*tiles*256 uint32 and is
 // cleared here.
 static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
-                                       long long n, int total_bits, uint32_t* aux, int num_sms, cudaStream_t stream) {
+                                       long long n, int total_bits, uint32_t* aux, int num_sms, cudaStream_t stream,
+                                       const char* hist_name = "sort_hist", const char* pass_name = "sort_pass") {
     if (n <= 0) return true;
     SortPlan plan = make_sort_plan(total_bits);
     size_t tiles = sort_num_tiles(n);
@@ -221,13 +222,17 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
     int hgrid = (int)((n + 256 * 4 * 8 - 1) / (256 * 4 * 8));
     if (hgrid > num_sms * 8) hgrid = num_sms * 8;
     if (hgrid < 1) hgrid = 1;
-    sort_histogram_kernel<<<hgrid, 256, 0, stream>>>(keys_a, (uint32_t)n, plan, hist);
+    {
+        ProfScope ps(hist_name, stream);
+        sort_histogram_kernel<<<hgrid, 256, 0, stream>>>(keys_a, (uint32_t)n, plan, hist);
+    }
     bool in_a = true;
     for (int p = 0; p < plan.passes; ++p) {
         const uint32_t* ki = in_a ? keys_a : keys_b;
         const uint32_t* vi = in_a ? vals_a : vals_b;
         uint32_t* ko = in_a ? keys_b : keys_a;
         uint32_t* vo = in_a ? vals_b : vals_a;
+        ProfScope ps(pass_name, stream);
         onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
             ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p,
             lookback + (size_t)p * tiles * 256);

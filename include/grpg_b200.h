@@ -191,6 +191,12 @@ int grpg_visible_filter(int P, int width, int height,
 int grpg_debug_reference_keys(int P, long long num_rendered, const void* geom_ws,
                               const void* binning_ws, uint64_t* keys_out, void* stream);
 
+/* Optional per-kernel timing: between begin and end every kernel this library launches is
+ * bracketed by CUDA events on its launching stream.  grpg_profile_end synchronises and writes
+ * "name:launches:total_ms" lines into buf.  Used by bench.py for the roofline object only. */
+int grpg_profile_begin(void);
+int grpg_profile_end(char* buf, size_t buf_len);
+
 const char* grpg_last_error(void);
 int grpg_version(void);
 
