@@ -22,8 +22,8 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
                               uint32_t* offsets, void* scratch, unsigned long long* num_rendered_dev, int num_sms,
                               cudaStream_t stream);
 void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tiles, const uint32_t* sorted_idx,
-                          const uint32_t* offsets, const uint2* rect, uint32_t* tile_keys, uint32_t* point_list,
-                          void* scratch, uint2* ranges, int num_sms, cudaStream_t stream);
+                          const uint32_t* offsets, const uint2* rect, const void* geom_scratch, uint32_t* tile_keys,
+                          uint32_t* point_list, void* scratch, uint2* ranges, int num_sms, cudaStream_t stream);
 void launch_reference_keys(long long R, const uint32_t* point_list, const uint32_t* tile_keys, const Rec* rec,
                            unsigned long long* keys, cudaStream_t stream);
 // blend_fwd.cu / blend_bwd.cu / preprocess_bwd.cu
@@ -235,7 +235,7 @@ int grpg_forward_render(const grpg_forward_args* a, int num_rendered) {
     char* g = (char*)a->geom_ws;
     char* b = (char*)a->binning_ws;
     run_instance_binning(a->P, num_rendered, gx, gx * gy, (const uint32_t*)(g + L.sorted_idx),
-                         (const uint32_t*)(g + L.offsets), (const uint2*)(g + L.rect),
+                         (const uint32_t*)(g + L.offsets), (const uint2*)(g + L.rect), g + L.scratch,
                          b ? (uint32_t*)(b + BL.tile_keys) : nullptr, b ? (uint32_t*)(b + BL.point_list) : nullptr,
                          b ? b + BL.scratch : nullptr, (uint2*)(im + IL.ranges), device_sm_count(), stream);
     if (a->debug) if (int rc = check_cuda("binning", true, stream)) return rc;

@@ -19,6 +19,8 @@ namespace grpg {
 // ---- 2. exclusive scan of tiles_touched in sorted order (decoupled look-back) ------------
 constexpr int SCAN_IPT = 8;
 constexpr int SCAN_TILE = 256 * SCAN_IPT;
+constexpr uint32_t EMIT_CHUNK = 4096;                      // instances emitted per warp
+constexpr uint32_t EMIT_MAX_CHUNKS = (1u << 30) / EMIT_CHUNK + 2;  // R < 2^30 is enforced by the API
 constexpr unsigned long long SC_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long SC_FLAG_PREFIX = 2ull << 62;
 constexpr unsigned long long SC_FLAG_MASK = 3ull << 62;
@@ -37,7 +39,8 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
                                                          uint32_t* __restrict__ offsets,
                                                          unsigned long long* __restrict__ status /*[tiles+1]*/,
                                                          uint32_t* __restrict__ tile_counter,
-                                                         unsigned long long* __restrict__ total_out) {
+                                                         unsigned long long* __restrict__ total_out,
+                                                         uint32_t* __restrict__ chunk_start) {
     __shared__ uint32_t s_scan[8];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_excl;
@@ -78,56 +81,71 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
 #pragma unroll
     for (int i = 0; i < SCAN_IPT; ++i) {
         uint32_t j = base + i;
-        if (j < P) offsets[j] = run;
+        if (j < P) {
+            offsets[j] = run;
+            // every multiple of EMIT_CHUNK inside [run, run + v) starts in sorted position j
+            for (uint32_t kb = (run + EMIT_CHUNK - 1) / EMIT_CHUNK; (unsigned long long)kb * EMIT_CHUNK < (unsigned long long)run + v[i]; ++kb)
+                chunk_start[kb] = j;
+        }
         run += v[i];
     }
 }
 
 // ---- 3. instance emission ------------------------------------------------------------------
-// One warp owns 32 consecutive depth-sorted Gaussians and writes their instances as one
-// contiguous run, 32 instances per step, so a splat covering thousands of tiles is spread
-// over the whole warp instead of one thread (reference: one thread loops over all its tiles,
-// rasterizer_impl.cu:98-109).
+// Output-balanced: warp k writes instances [k*EMIT_CHUNK, (k+1)*EMIT_CHUNK) no matter how they are
+// distributed over Gaussians (a splat covering the whole screen is shared by many warps; the
+// reference gives all of its tiles to one thread, rasterizer_impl.cu:98-109).  The scan kernel
+// recorded the depth-sorted position that owns each chunk boundary, so no search is needed.
 __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __restrict__ sorted_idx,
                                                              const uint32_t* __restrict__ offsets,
-                                                             const uint2* __restrict__ rect, uint32_t P,
-                                                             uint32_t grid_x, uint32_t* __restrict__ inst_tile,
+                                                             const uint2* __restrict__ rect,
+                                                             const uint32_t* __restrict__ chunk_start, uint32_t P,
+                                                             uint32_t R, uint32_t grid_x,
+                                                             uint32_t* __restrict__ inst_tile,
                                                              uint32_t* __restrict__ inst_gauss) {
     const int lane = threadIdx.x & 31;
-    const uint32_t pos = (blockIdx.x * blockDim.x + threadIdx.x);  // sorted position of this lane's Gaussian
-    uint32_t g = 0, off = 0, x0 = 0, y0 = 0, w = 0, cnt = 0;
-    if (pos < P) {
-        g = sorted_idx[pos];
-        off = offsets[pos];
-        uint2 r = rect[g];
-        x0 = r.x & 0xffffu; y0 = r.y & 0xffffu;
-        w = (r.x >> 16) - x0;
-        cnt = w * ((r.y >> 16) - y0);
-    }
-    const uint32_t run_start = __shfl_sync(0xffffffffu, off, 0);
-    // exclusive offset inside the warp's run; lanes past P never own an instance
-    const uint32_t rel = pos < P ? off - run_start : 0xFFFFFFFFu;
-    const uint32_t run_len = __reduce_max_sync(0xffffffffu, pos < P ? rel + cnt : 0u);
-    for (uint32_t k0 = 0; k0 < run_len; k0 += 32) {
-        const uint32_t k = k0 + lane;
-        // owner = last lane whose rel <= k (rel is non-decreasing)
-        int owner = 0;
+    const uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long lo64 = (unsigned long long)chunk * EMIT_CHUNK;
+    if (lo64 >= R) return;
+    uint32_t cur = (uint32_t)lo64;
+    const uint32_t hi = min(R, cur + EMIT_CHUNK);
+    uint32_t pos = chunk_start[chunk];
+    while (cur < hi && pos < P) {
+        const uint32_t p = pos + lane;
+        uint32_t g = 0, off = 0xFFFFFFFFu, x0 = 0, y0 = 0, w = 1, end = 0;
+        if (p < P) {
+            g = sorted_idx[p];
+            off = offsets[p];
+            const uint2 r = rect[g];
+            x0 = r.x & 0xffffu; y0 = r.y & 0xffffu;
+            w = (r.x >> 16) - x0;
+            end = off + w * ((r.y >> 16) - y0);
+            if (w == 0) w = 1;
+        }
+        const uint32_t group_end = __reduce_max_sync(0xffffffffu, end);
+        const uint32_t stop = min(hi, group_end);
+        for (uint32_t k0 = cur; k0 < stop; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            int owner = 0;  // last lane whose offset <= k (offsets are non-decreasing across lanes)
 #pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-            uint32_t probe = __shfl_sync(0xffffffffu, rel, (owner + step) & 31);
-            if (owner + step < 32 && probe <= k) owner += step;
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t probe = __shfl_sync(0xffffffffu, off, (owner + step) & 31);
+                if (probe <= k) owner += step;
+            }
+            const uint32_t o_off = __shfl_sync(0xffffffffu, off, owner);
+            const uint32_t o_w = __shfl_sync(0xffffffffu, w, owner);
+            const uint32_t o_x0 = __shfl_sync(0xffffffffu, x0, owner);
+            const uint32_t o_y0 = __shfl_sync(0xffffffffu, y0, owner);
+            const uint32_t o_g = __shfl_sync(0xffffffffu, g, owner);
+            if (k < stop) {
+                const uint32_t m = k - o_off;
+                const uint32_t ty = m / o_w, tx = m - ty * o_w;
+                inst_tile[k] = (o_y0 + ty) * grid_x + (o_x0 + tx);
+                inst_gauss[k] = o_g;
+            }
         }
-        const uint32_t o_rel = __shfl_sync(0xffffffffu, rel, owner);
-        const uint32_t o_w = __shfl_sync(0xffffffffu, w, owner);
-        const uint32_t o_x0 = __shfl_sync(0xffffffffu, x0, owner);
-        const uint32_t o_y0 = __shfl_sync(0xffffffffu, y0, owner);
-        const uint32_t o_g = __shfl_sync(0xffffffffu, g, owner);
-        if (k < run_len) {
-            const uint32_t m = k - o_rel;
-            const uint32_t ty = m / o_w, tx = m - ty * o_w;
-            inst_tile[run_start + k] = (o_y0 + ty) * grid_x + (o_x0 + tx);
-            inst_gauss[run_start + k] = o_g;
-        }
+        if (stop > cur) cur = stop;
+        pos += 32;
     }
 }
 
@@ -167,6 +185,7 @@ size_t geom_scratch_bytes(int P) {
     b += align_up((size_t)SORT_MAX_PASSES * (256 + 64) * 4 + (size_t)SORT_MAX_PASSES * sort_num_tiles(P) * 256 * 4, 256);
     b += align_up(((size_t)(P + SCAN_TILE - 1) / SCAN_TILE + 2) * 8, 256);
     b += 256;  // scan tile counter + total
+    b += align_up((size_t)EMIT_MAX_CHUNKS * 4, 256);  // chunk_start
     return b;
 }
 size_t binning_scratch_bytes(long long R) {
@@ -189,6 +208,8 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
     size_t scan_tiles = ((size_t)P + SCAN_TILE - 1) / SCAN_TILE;
     p += align_up((scan_tiles + 2) * 8, 256);
     uint32_t* scan_counter = (uint32_t*)p;
+    p += 256;
+    uint32_t* chunk_start = (uint32_t*)p;
 
     {
         ProfScope ps("iota", stream);
@@ -203,13 +224,13 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
     cudaMemsetAsync(status, 0, (scan_tiles + 2) * 8 + 256, stream);
     ProfScope ps("scan_tiles", stream);
     scan_tiles_kernel<<<(unsigned)scan_tiles, 256, 0, stream>>>(sorted_idx, tiles_touched, (uint32_t)P, offsets, status,
-                                                                 scan_counter, num_rendered_dev);
+                                                                 scan_counter, num_rendered_dev, chunk_start);
 }
 
 // Steps 3-5.  Final order lands in (tile_keys, point_list).
 void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tiles, const uint32_t* sorted_idx,
-                          const uint32_t* offsets, const uint2* rect, uint32_t* tile_keys, uint32_t* point_list,
-                          void* scratch, uint2* ranges, int num_sms, cudaStream_t stream) {
+                          const uint32_t* offsets, const uint2* rect, const void* geom_scratch, uint32_t* tile_keys,
+                          uint32_t* point_list, void* scratch, uint2* ranges, int num_sms, cudaStream_t stream) {
     cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), stream);
     if (R <= 0) return;
     char* p = (char*)scratch;
@@ -227,7 +248,15 @@ void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tile
     uint32_t* v1 = start_in_final ? vals_b : point_list;
     {
         ProfScope ps("emit_instances", stream);
-        emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(sorted_idx, offsets, rect, (uint32_t)P, grid_x, k0, v0);
+        // chunk_start lives at the end of the geometry scratch (see run_depth_order_and_scan)
+        const char* gs = (const char*)geom_scratch;
+        gs += align_up((size_t)P * 4, 256) * 2;
+        gs += align_up((size_t)SORT_MAX_PASSES * (256 + 64) * 4 + (size_t)SORT_MAX_PASSES * sort_num_tiles(P) * 256 * 4, 256);
+        gs += align_up((((size_t)P + SCAN_TILE - 1) / SCAN_TILE + 2) * 8, 256) + 256;
+        const uint32_t* chunk_start = (const uint32_t*)gs;
+        const unsigned warps = (unsigned)((R + EMIT_CHUNK - 1) / EMIT_CHUNK);
+        emit_instances_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(sorted_idx, offsets, rect, chunk_start, (uint32_t)P,
+                                                                   (uint32_t)R, grid_x, k0, v0);
     }
     onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream, "tile_sort_hist", "tile_sort_pass");
     ProfScope ps("tile_ranges", stream);

@@ -23,6 +23,38 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Sums 16 per-lane values over the warp with 16 shuffles instead of 80: at every butterfly step a
+// lane hands half of its remaining slots to its partner and keeps the other half, so after the
+// xor-16/8/4/2 steps each lane owns ONE slot and the xor-1 step completes it.  On return the lane
+// holds the warp total of slot ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1).
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = h4 ? v[i] : v[i + 8];
+        const float keep = h4 ? v[i + 8] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h3 ? a[i] : a[i + 4];
+        const float keep = h3 ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h2 ? b[i] : b[i + 2];
+        const float keep = h2 ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float send = h1 ? c[0] : c[1];
+    const float keep = h1 ? c[1] : c[0];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
 template <int SB>
 __global__ void __launch_bounds__(256) blend_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const Rec* __restrict__ rec,
@@ -176,20 +208,13 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                     g_cw = -0.5f * gdy * dy * dL_dG;
                     g_op = G * dL_dopa;
                 }
-                // warp reduction, then one vector of atomics per (warp, Gaussian)
-                g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_mabs = warp_sum(g_mabs);
-                g_cx = warp_sum(g_cx); g_cy = warp_sum(g_cy); g_cw = warp_sum(g_cw);
-                g_op = warp_sum(g_op);
-                g_c0 = warp_sum(g_c0); g_c1 = warp_sum(g_c1); g_c2 = warp_sum(g_c2);
-                g_d = warp_sum(g_d);
-                float mine = 0.f;
-                switch (lane) {
-                    case 0: mine = g_mx; break;   case 1: mine = g_my; break;  case 2: mine = g_mabs; break;
-                    case 3: mine = g_cx; break;   case 4: mine = g_cy; break;  case 5: mine = g_cw; break;
-                    case 6: mine = g_op; break;   case 7: mine = g_c0; break;  case 8: mine = g_c1; break;
-                    case 9: mine = g_c2; break;   case 10: mine = g_d; break;  default: break;
-                }
-                if (lane < 11) atomicAdd(grad_rec + (size_t)gid * GREC + lane, mine);
+                // warp reduction (16-slot butterfly), then one vector of atomics per (warp, Gaussian):
+                // even lanes own one component each of the 48-byte gradient record
+                const float vals[16] = {g_mx, g_my, g_mabs, g_cx, g_cy, g_cw, g_op, g_c0, g_c1, g_c2, g_d,
+                                        0.f, 0.f, 0.f, 0.f, 0.f};
+                const float mine = warp_reduce16(vals, lane);
+                const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                if (!(lane & 1) && slot < 11) atomicAdd(grad_rec + (size_t)gid * GREC + slot, mine);
                 if (SB > 0) {
 #pragma unroll
                     for (int i = 0; i < SB; ++i) {

@@ -61,6 +61,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             _C.rasterize_gaussians, native_args, rs.debug, "snapshot_fw.dump", "forward")
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
+        ctx.tensor_inputs = [isinstance(t, torch.Tensor) for t in (means3D, means2D, sh, colors_precomp, semantics,
+                                                                   opacities, scales, rotations, cov3Ds_precomp)]
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning,
                               img, alpha, semantics)
         ctx.mark_non_differentiable(radii)
@@ -79,7 +81,9 @@ class _RasterizeGaussians(torch.autograd.Function):
             _C.rasterize_gaussians_backward, native_args, rs.debug, "snapshot_bw.dump", "backward")
         # order of forward()'s inputs: means3D, means2D, sh, colors_precomp, semantics, opacities, scales,
         # rotations, cov3Ds_precomp, raster_settings
-        return g_means3D, g_means2D, g_sh, g_colors, g_sem, g_opac, g_scales, g_rot, g_cov3D, None
+        grads = (g_means3D, g_means2D, g_sh, g_colors, g_sem, g_opac, g_scales, g_rot, g_cov3D)
+        # autograd rejects a gradient for an argument that was not a tensor (e.g. means2D=None in eval)
+        return tuple(g if is_t else None for g, is_t in zip(grads, ctx.tensor_inputs)) + (None,)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,

@@ -219,9 +219,10 @@ def render(sc, dtype=torch.float64, requires_grad=False, tile_subset=None):
     return img, leaves, pre
 
 
-def time_tiles(pre_np, binned, sc, tile_ids, dtype=torch.float32):
+def time_tiles(pre_np, binned, sc, tile_ids, dtype=torch.float32, budget_s=20.0):
     """Time the per-pixel blend (forward + autograd backward) of the given tiles, starting from the C oracle's
-    per-Gaussian outputs and instance order.  Returns seconds.  (bench.py cpu_baseline leg.)"""
+    per-Gaussian outputs and instance order; stops once `budget_s` seconds are spent.
+    Returns (seconds, instances_processed, tiles_processed).  (bench.py cpu_baseline leg.)"""
     import time as _time
     W, H = sc.width, sc.height
     gx = (W + 15) // 16
@@ -233,8 +234,13 @@ def time_tiles(pre_np, binned, sc, tile_ids, dtype=torch.float32):
     bg = sc.bg.to(dtype)
     plist = torch.from_numpy(binned["point_list"].astype("int64"))
     t0 = _time.time()
+    n_inst = n_tiles = 0
     for t in tile_ids:
+        if _time.time() - t0 > budget_s and n_tiles >= 2:
+            break
         lo, hi = int(binned["ranges"][t, 0]), int(binned["ranges"][t, 1])
+        n_inst += hi - lo
+        n_tiles += 1
         ids = plist[lo:hi]
         lp = pix[ids].clone().requires_grad_(True)
         lc = conic[ids].clone().requires_grad_(True)
@@ -271,4 +277,4 @@ def time_tiles(pre_np, binned, sc, tile_ids, dtype=torch.float32):
         loss = (C + T * bg[:, None, None]).sum() + 0.01 * D.sum() + 0.1 * Wt.sum()
         if loss.requires_grad:
             loss.backward()
-    return _time.time() - t0
+    return _time.time() - t0, n_inst, n_tiles

@@ -32,6 +32,8 @@ def test_oracle_matches_reference_golden(name):
         assert np.array_equal(binned["keys"], gold["point_list_keys"].astype(np.uint64))
     assert np.array_equal(binned["ranges"], gold["ranges"].astype(np.uint32))
     for k in ("depths", "means2D", "conic_opacity", "rgb"):
+        if k == "rgb" and sc.colors_precomp is not None:
+            continue  # never written by the reference on the colors_precomp path (forward.cu:241)
         assert np.array_equal(pre[k][vis].view(np.uint32), gold[k][vis].view(np.uint32)), k
     if sc.cov3D_precomp is None:
         assert np.array_equal(pre["cov3D"][vis].view(np.uint32), gold["cov3D"][vis].view(np.uint32))
@@ -41,9 +43,9 @@ def test_oracle_matches_reference_golden(name):
     for k in ("color", "depth", "alpha", "semantic"):
         if gold[k].size:
             assert float(np.abs(img[k] - gold[k]).max()) <= 1e-4, k
-    for n in cases.GRAD_NAMES:
+    for n in cases.GRAD_NAMES:  # double accumulation here vs float atomics there: see test_parity_gpu.py
         if gold[n].size:
-            assert cases.rel_err(grads[n], gold[n]) <= 1e-3, n
+            assert cases.rel_err(grads[n], gold[n]) <= 3e-3, n
 
 
 @pytest.mark.parametrize("S,white", [(0, False), (3, True)])
