@@ -55,13 +55,17 @@ def _layouts(P: int, R: int, W: int, H: int):
 
 def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
-                        degree, campos, prefiltered, debug
+                        degree, campos, prefiltered, debug, *, _band=(1, 0)
                         ) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
                                    torch.Tensor, torch.Tensor, torch.Tensor]:
     """RasterizeGaussiansCUDA (rasterize_points.cu:35-124).
 
     Returns (num_rendered, color[3,H,W], depth[1,H,W], alpha[1,H,W], semantic[S,H,W], radii[P],
     geomBuffer, binningBuffer, imgBuffer).
+
+    `_band=(stride, phase)` (keyword-only, not part of the reference surface) restricts the call to the tile
+    rows r with r % stride == phase; the images then use the compact band layout [C, rows*16, W]
+    (gaussianrpg_b200.dist reassembles them).
     """
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:58-60
@@ -95,14 +99,18 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
     bg_c, view_c, proj_c, cam_c = _f32(background), _f32(viewmatrix), _f32(projmatrix), _f32(campos)
     keep += [bg_c, view_c, proj_c, cam_c]
 
-    # every pixel / Gaussian row is written by the kernels: no zero fill needed
-    out_color = torch.empty((NUM_CHANNELS, H, W), **f32)
-    out_depth = torch.empty((1, H, W), **f32)
-    out_alpha = torch.empty((1, H, W), **f32)
-    out_semantic = torch.empty((S, H, W), **f32)
+    stride, phase = int(_band[0]), int(_band[1])
+    HL = lib.grpg_band_height(H, stride, phase)
+    # every pixel / Gaussian row is written by the kernels: no zero fill needed (band images are padded to
+    # whole tiles, so zero them when the last tile row is ragged)
+    alloc = torch.zeros if (stride > 1 and H % 16 != 0) else torch.empty
+    out_color = alloc((NUM_CHANNELS, HL, W), **f32)
+    out_depth = alloc((1, HL, W), **f32)
+    out_alpha = alloc((1, HL, W), **f32)
+    out_semantic = alloc((S, HL, W), **f32)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
 
-    gl, _, il = _layouts(P, 0, W, H)
+    gl, _, il = _layouts(P, 0, W, HL)
     geom = torch.empty(gl.total_bytes, **u8)
     img = torch.empty(il.total_bytes, **u8)
 
@@ -120,6 +128,7 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
     a.radii = radii.data_ptr()
     a.geom_ws, a.image_ws, a.binning_ws = geom.data_ptr(), img.data_ptr(), None
     a.stream = _stream()
+    a.tile_row_stride, a.tile_row_phase = stride, phase
 
     with torch.cuda.device(dev):
         n = C.c_int(0)
@@ -136,28 +145,48 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                  dL_dout_depth, dL_dout_alpha, dL_dout_semantic, sh, degree, campos, geomBuffer, R,
-                                 binningBuffer, imageBuffer, alphas, semantics, debug):
+                                 binningBuffer, imageBuffer, alphas, semantics, debug, *, _band=(1, 0), _height=None,
+                                 _stage=3, _grad_rec=None, _slice=None):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:126-220).
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
     dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4], dL_dsemantic[P,S]).
+
+    Keyword-only extras for the multi-GPU path (gaussianrpg_b200.dist): `_band` as in the forward (the pixel
+    gradients and `alphas` are then band images and `_height` is the frame height); `_stage=1` runs only the
+    blend backward and returns (grad_rec[P,12], dL_dsemantic[P,S]); `_stage=2` runs only the per-Gaussian
+    backward for `_slice=(p_begin, p_count)` from `_grad_rec[p_count,12]` and returns p_count-row gradients.
     """
     _require_cuda()
     lib = _lib.load()
     dev = means3D.device
     P = int(means3D.shape[0])
-    H, W = int(dL_dout_color.shape[1]), int(dL_dout_color.shape[2])
-    S = int(dL_dout_semantic.shape[0])
+    stride, phase = int(_band[0]), int(_band[1])
+    if _stage & 1:
+        H, W = int(dL_dout_color.shape[1]), int(dL_dout_color.shape[2])
+        S = int(dL_dout_semantic.shape[0])
+    else:
+        H, W = 16, 16  # unused by the geometry stage
+        S = int(semantics.shape[1]) if semantics is not None and semantics.ndim == 2 else 0
+    if _height is not None:
+        H = int(_height)
     M = int(sh.shape[1]) if sh is not None and sh.numel() != 0 else 0
     f32 = dict(dtype=torch.float32, device=dev)
+    p_begin, p_count = (0, P) if _slice is None else (int(_slice[0]), int(_slice[1]))
+    Pout = P if _stage != 2 else p_count
 
     def out(*shape):  # fully written by grpg_backward
         return torch.empty(shape, **f32) if P != 0 else torch.zeros(shape, **f32)
 
+    if _stage == 1:
+        Pout = 0  # no per-parameter outputs in the blend-only stage
+    P_full = P
+    P = Pout
     dL_dmeans3D, dL_dmeans2D, dL_dcolors = out(P, 3), out(P, 3), out(P, NUM_CHANNELS)
     dL_ddepths, dL_dconic, dL_dopacity = out(P, 1), out(P, 2, 2), out(P, 1)
     dL_dcov3D, dL_dsh, dL_dscales, dL_drot = out(P, 6), out(P, M, 3), out(P, 3), out(P, 4)
-    dL_dsemantic = out(P, S)
+    dL_dsemantic = out(P_full if _stage != 2 else P, S)
+    P = P_full
     if P == 0:
         return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot,
                 dL_dsemantic)
@@ -190,11 +219,18 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     a.dL_dcolor, a.dL_ddepth, a.dL_dmean3D = dL_dcolors.data_ptr(), dL_ddepths.data_ptr(), dL_dmeans3D.data_ptr()
     a.dL_dcov3D, a.dL_dsh = dL_dcov3D.data_ptr(), _ptr(dL_dsh)
     a.dL_dscale, a.dL_drot, a.dL_dsemantic = dL_dscales.data_ptr(), dL_drot.data_ptr(), _ptr(dL_dsemantic)
-    grad_ws = torch.empty(lib.grpg_backward_workspace_bytes(P, S), dtype=torch.uint8, device=dev)
+    if _grad_rec is not None:
+        grad_ws = _grad_rec.contiguous()
+    else:
+        grad_ws = torch.empty((P, 12), dtype=torch.float32, device=dev)
     a.grad_ws = grad_ws.data_ptr()
     a.stream = _stream()
+    a.tile_row_stride, a.tile_row_phase = stride, phase
+    a.stages, a.p_begin, a.p_count = int(_stage), p_begin, p_count
     with torch.cuda.device(dev):
         _check(lib.grpg_backward(C.byref(a)))
+    if _stage == 1:
+        return grad_ws, dL_dsemantic
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot, dL_dsemantic
 
 

@@ -41,6 +41,7 @@ class ForwardArgs(C.Structure):
         ("viewmatrix", _fp), ("projmatrix", _fp), ("cam_pos", _fp),
         ("out_color", _fp), ("out_depth", _fp), ("out_alpha", _fp), ("out_semantic", _fp), ("radii", _fp),
         ("geom_ws", _fp), ("binning_ws", _fp), ("image_ws", _fp), ("stream", _fp),
+        ("tile_row_stride", C.c_int), ("tile_row_phase", C.c_int),
     ]
 
 
@@ -57,6 +58,8 @@ class BackwardArgs(C.Structure):
         ("dL_dmean2D", _fp), ("dL_dconic", _fp), ("dL_dopacity", _fp), ("dL_dcolor", _fp), ("dL_ddepth", _fp),
         ("dL_dmean3D", _fp), ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dscale", _fp), ("dL_drot", _fp),
         ("dL_dsemantic", _fp), ("grad_ws", _fp), ("stream", _fp),
+        ("tile_row_stride", C.c_int), ("tile_row_phase", C.c_int), ("stages", C.c_int), ("p_begin", C.c_int),
+        ("p_count", C.c_int),
     ]
 
 
@@ -65,6 +68,8 @@ SYMBOLS = {
     "grpg_get_geometry_layout": (C.c_int, [C.c_int, C.POINTER(GeomLayout)]),
     "grpg_get_binning_layout": (C.c_int, [C.c_longlong, C.POINTER(BinningLayout)]),
     "grpg_get_image_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(ImageLayout)]),
+    "grpg_band_rows": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "grpg_band_height": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "grpg_forward_geometry": (C.c_int, [C.POINTER(ForwardArgs), C.POINTER(C.c_int)]),
     "grpg_forward_render": (C.c_int, [C.POINTER(ForwardArgs), C.c_int]),
     "grpg_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

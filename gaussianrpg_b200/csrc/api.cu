@@ -130,6 +130,9 @@ int grpg_profile_end(char* buf, size_t buf_len) {
 }
 int grpg_version(void) { return 100; }
 
+int grpg_band_rows(int height, int stride, int phase) { return band_rows(height, stride, phase); }
+int grpg_band_height(int height, int stride, int phase) { return band_height(height, stride, phase); }
+
 int grpg_get_geometry_layout(int P, grpg_geom_layout* out) {
     if (!out || P < 0) return fail("grpg_get_geometry_layout: bad arguments");
     size_t o = 0;
@@ -189,6 +192,8 @@ static int validate_forward(const grpg_forward_args* a) {
     if (a->S < 0 || (a->S > 0 && (!a->semantics || !a->out_semantic))) return fail("bad semantics arguments");
     if ((a->width + 15) / 16 > 65535 || (a->height + 15) / 16 > 65535) return fail("image too large (tile grid > 65535)");
     if (!a->geom_ws || !a->image_ws || !a->radii) return fail("missing workspace");
+    if (a->tile_row_stride > 1 && (a->tile_row_phase < 0 || a->tile_row_phase >= a->tile_row_stride))
+        return fail("tile_row_phase must lie in [0, tile_row_stride)");
     return 0;
 }
 
@@ -222,10 +227,11 @@ int grpg_forward_geometry(const grpg_forward_args* a, int* num_rendered) {
 int grpg_forward_render(const grpg_forward_args* a, int num_rendered) {
     if (int rc = validate_forward(a)) return rc;
     cudaStream_t stream = (cudaStream_t)a->stream;
+    const int stride = a->tile_row_stride > 1 ? a->tile_row_stride : 1, phase = a->tile_row_stride > 1 ? a->tile_row_phase : 0;
     grpg_image_layout IL;
-    grpg_get_image_layout(a->width, a->height, &IL);
+    grpg_get_image_layout(a->width, band_height(a->height, stride, phase), &IL);
     char* im = (char*)a->image_ws;
-    const uint32_t gx = (a->width + 15) / 16, gy = (a->height + 15) / 16;
+    const uint32_t gx = (a->width + 15) / 16, gy = (uint32_t)band_rows(a->height, stride, phase);
     if (a->P == 0) return 0;
     if (num_rendered > 0 && !a->binning_ws) return fail("missing binning workspace");
     grpg_geom_layout L;
@@ -249,33 +255,44 @@ size_t grpg_backward_workspace_bytes(int P, int S) {
     return align_up((size_t)P * 12 * sizeof(float), 256);
 }
 
-int grpg_backward(const grpg_backward_args* a) {
-    if (!a) return fail("null arguments");
-    if (a->P == 0) return 0;
+int grpg_backward(const grpg_backward_args* a_in) {
+    if (!a_in) return fail("null arguments");
+    if (a_in->P == 0) return 0;
+    grpg_backward_args args = *a_in;
+    grpg_backward_args* a = &args;
+    if (a->stages == 0) a->stages = 3;
+    if (a->stages == 3) { a->p_begin = 0; a->p_count = a->P; }
     if (a->S > GRPG_MAX_SEMANTIC_BWD)
         return fail("backward supports at most 32 semantic channels (reference NUM_CLASSES is 20, config.h:16)");
-    if (!a->grad_ws || !a->geom_ws || !a->image_ws) return fail("missing workspace");
+    if (!a->grad_ws || !a->geom_ws) return fail("missing workspace");
+    if (a->p_begin < 0 || a->p_count < 0 || a->p_begin + a->p_count > a->P) return fail("bad Gaussian slice");
     cudaStream_t stream = (cudaStream_t)a->stream;
+    const int stride = a->tile_row_stride > 1 ? a->tile_row_stride : 1, phase = a->tile_row_stride > 1 ? a->tile_row_phase : 0;
     grpg_geom_layout L;
     grpg_get_geometry_layout(a->P, &L);
-    grpg_binning_layout BL;
-    grpg_get_binning_layout(a->R, &BL);
-    grpg_image_layout IL;
-    grpg_get_image_layout(a->width, a->height, &IL);
     const char* g = (const char*)a->geom_ws;
-    const char* b = (const char*)a->binning_ws;
-    const char* im = (const char*)a->image_ws;
     float* grad_rec = (float*)a->grad_ws;
-    cudaMemsetAsync(grad_rec, 0, (size_t)a->P * 12 * sizeof(float), stream);
-    if (a->S > 0) cudaMemsetAsync(a->dL_dsemantic, 0, (size_t)a->P * a->S * sizeof(float), stream);
-    if (a->R > 0) {
-        if (!b) return fail("missing binning workspace");
-        launch_blend_bwd(a, (const uint2*)(im + IL.ranges), (const uint32_t*)(b + BL.point_list), (const Rec*)(g + L.rec),
-                         (const uint32_t*)(im + IL.n_contrib), grad_rec, stream);
-        if (a->debug) if (int rc = check_cuda("blend backward", true, stream)) return rc;
+    if (a->stages & 1) {
+        if (!a->image_ws) return fail("missing image workspace");
+        grpg_binning_layout BL;
+        grpg_get_binning_layout(a->R, &BL);
+        grpg_image_layout IL;
+        grpg_get_image_layout(a->width, band_height(a->height, stride, phase), &IL);
+        const char* b = (const char*)a->binning_ws;
+        const char* im = (const char*)a->image_ws;
+        cudaMemsetAsync(grad_rec, 0, (size_t)a->P * 12 * sizeof(float), stream);
+        if (a->S > 0) cudaMemsetAsync(a->dL_dsemantic, 0, (size_t)a->P * a->S * sizeof(float), stream);
+        if (a->R > 0) {
+            if (!b) return fail("missing binning workspace");
+            launch_blend_bwd(a, (const uint2*)(im + IL.ranges), (const uint32_t*)(b + BL.point_list),
+                             (const Rec*)(g + L.rec), (const uint32_t*)(im + IL.n_contrib), grad_rec, stream);
+            if (a->debug) if (int rc = check_cuda("blend backward", true, stream)) return rc;
+        }
     }
-    const float* cov3D = a->cov3D_precomp ? a->cov3D_precomp : (const float*)(g + L.cov3d);
-    launch_preprocess_bwd(a, cov3D, (const uint8_t*)(g + L.clamped), grad_rec, stream);
+    if (a->stages & 2) {
+        const float* cov3D = a->cov3D_precomp ? a->cov3D_precomp : (const float*)(g + L.cov3d);
+        launch_preprocess_bwd(a, cov3D, (const uint8_t*)(g + L.clamped), grad_rec, stream);
+    }
     return check_cuda("backward", a->debug != 0, stream);
 }
 

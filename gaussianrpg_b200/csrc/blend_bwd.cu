@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dalphas,
     const float* __restrict__ dL_dpixel_semantics, float* __restrict__ grad_rec /*[P][12]*/,
-    float* __restrict__ dL_dsemantics /*[P][S]*/) {
+    float* __restrict__ dL_dsemantics /*[P][S]*/, int HL, int row_stride, int row_phase) {
     __shared__ float4 s_a[BWD_BATCH];
     __shared__ float4 s_b[BWD_BATCH];
     __shared__ float4 s_c[BWD_BATCH];
@@ -73,13 +73,14 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
     const uint32_t tile = blockIdx.y * tiles_x + blockIdx.x;
     const int bx0 = blockIdx.x * GRPG_TILE + (warp & 1) * 8;
-    const int by0 = blockIdx.y * GRPG_TILE + (warp >> 1) * 4;
+    const int by0 = (blockIdx.y * row_stride + row_phase) * GRPG_TILE + (warp >> 1) * 4;
     const int pix_x = bx0 + (lane & 7), pix_y = by0 + (lane >> 3);
+    const int loc_y = blockIdx.y * GRPG_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = pix_x < W && pix_y < H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
     const float bx_lo = (float)bx0, bx_hi = (float)(bx0 + 7), by_lo = (float)by0, by_hi = (float)(by0 + 3);
-    const size_t hw = (size_t)H * W;
-    const size_t pid = (size_t)pix_y * W + pix_x;
+    const size_t hw = (size_t)HL * W;
+    const size_t pid = (size_t)loc_y * W + pix_x;
 
     const uint2 range = ranges[tile];
     const int n_inst = (int)(range.y - range.x);
@@ -231,13 +232,16 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
 
 void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const uint32_t* point_list, const Rec* rec,
                       const uint32_t* n_contrib, float* grad_rec, cudaStream_t stream) {
-    const dim3 grid((a->width + GRPG_TILE - 1) / GRPG_TILE, (a->height + GRPG_TILE - 1) / GRPG_TILE, 1);
+    const int stride = a->tile_row_stride > 1 ? a->tile_row_stride : 1, phase = a->tile_row_stride > 1 ? a->tile_row_phase : 0;
+    const int HL = band_height(a->height, stride, phase);
+    const dim3 grid((a->width + GRPG_TILE - 1) / GRPG_TILE, band_rows(a->height, stride, phase), 1);
+    if (grid.y == 0) return;
     const int S = a->S;
     ProfScope ps("blend_bwd", stream);
 #define GRPG_BWD_LAUNCH(SBV)                                                                                      \
     blend_bwd_kernel<SBV><<<grid, 256, 0, stream>>>(ranges, point_list, rec, a->semantics, S, a->width, a->height,  \
                                                      a->background, a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth, \
-                                                     a->dL_dalphas, a->dL_dpix_semantic, grad_rec, a->dL_dsemantic)
+                                                     a->dL_dalphas, a->dL_dpix_semantic, grad_rec, a->dL_dsemantic, HL, stride, phase)
     if (S == 0) GRPG_BWD_LAUNCH(0);
     else if (S <= 4) GRPG_BWD_LAUNCH(4);
     else if (S <= 8) GRPG_BWD_LAUNCH(8);

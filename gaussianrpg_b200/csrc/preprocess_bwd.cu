@@ -16,10 +16,12 @@ namespace grpg {
 
 struct f3 { float x, y, z; };
 
+// Inputs are full-size arrays indexed by the global Gaussian id p_begin + i; grad_rec and every output hold
+// `P` rows for the slice [p_begin, p_begin + P) (row i).
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
-    int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
-    const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
-    const float* __restrict__ rotations, float scale_modifier, const float* __restrict__ cov3Ds,
+    int P, int p_begin, int D, int M, const float* __restrict__ means3D_full, const int* __restrict__ radii_full,
+    const float* __restrict__ shs_full, const uint8_t* __restrict__ clamped_full, const float* __restrict__ scales_full,
+    const float* __restrict__ rotations_full, float scale_modifier, const float* __restrict__ cov3Ds_full,
     const float* __restrict__ view, const float* __restrict__ proj, float h_x, float h_y, float tan_fovx,
     float tan_fovy, const float* __restrict__ campos, const float* __restrict__ grad_rec /*[P][12]*/,
     float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic_out, float* __restrict__ dL_dopacity,
@@ -28,6 +30,15 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     float* __restrict__ dL_drot) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
+    // shift the input views to the slice so that everything below indexes with the local row `idx`
+    const size_t g0_ = (size_t)p_begin;
+    const float* means3D = means3D_full + 3 * g0_;
+    const int* radii = radii_full + g0_;
+    const float* shs = shs_full ? shs_full + g0_ * M * 3 : nullptr;
+    const uint8_t* clamped = clamped_full + g0_;
+    const float* scales = scales_full ? scales_full + 3 * g0_ : nullptr;
+    const float* rotations = rotations_full ? rotations_full + 4 * g0_ : nullptr;
+    const float* cov3Ds = cov3Ds_full + 6 * g0_;
     const bool vis = radii[idx] > 0;
 
     float4 g0 = make_float4(0, 0, 0, 0), g1 = g0, g2 = g0;
@@ -279,12 +290,13 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 
 void launch_preprocess_bwd(const grpg_backward_args* a, const float* cov3D, const uint8_t* clamped,
                            const float* grad_rec, cudaStream_t stream) {
-    const int P = a->P;
+    const int P = a->p_count;
+    if (P <= 0) return;
     const float focal_y = a->height / (2.0f * a->tan_fovy);
     const float focal_x = a->width / (2.0f * a->tan_fovx);
     ProfScope ps("preprocess_bwd", stream);
     preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
-        P, a->D, a->M, a->means3D, a->radii, a->shs, clamped, a->scales, a->rotations, a->scale_modifier, cov3D,
+        P, a->p_begin, a->D, a->M, a->means3D, a->radii, a->shs, clamped, a->scales, a->rotations, a->scale_modifier, cov3D,
         a->viewmatrix, a->projmatrix, focal_x, focal_y, a->tan_fovx, a->tan_fovy, a->cam_pos, grad_rec, a->dL_dmean2D,
         a->dL_dconic, a->dL_dopacity, a->dL_dcolor, a->dL_ddepth, a->dL_dmean3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscale,
         a->dL_drot);

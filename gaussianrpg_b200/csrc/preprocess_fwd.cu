@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
     const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
     int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
-    int prefiltered, int* __restrict__ radii, Rec* __restrict__ rec, uint32_t* __restrict__ depth_key,
+    int prefiltered, int row_stride, int row_phase, int* __restrict__ radii, Rec* __restrict__ rec, uint32_t* __restrict__ depth_key,
     uint2* __restrict__ rect, uint32_t* __restrict__ tiles_touched, float* __restrict__ cov3D_out,
     uint8_t* __restrict__ clamped) {
     __shared__ float s_cam[35];
@@ -291,9 +291,17 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     r.c = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
     rec[idx] = r;
     radii[idx] = o.radius;
-    tiles_touched[idx] = (o.xmax - o.xmin) * (o.ymax - o.ymin);
+    uint32_t ly0 = o.ymin, ly1 = o.ymax;
+    if (row_stride > 1) {
+        // rows of [ymin, ymax) owned by this band (r % stride == phase), expressed as local row indices
+        const uint32_t st = (uint32_t)row_stride, ph = (uint32_t)row_phase;
+        const uint32_t first = o.ymin + ((ph + st - o.ymin % st) % st);
+        if (first < o.ymax) { ly0 = (first - ph) / st; ly1 = ly0 + (o.ymax - 1 - first) / st + 1; }
+        else { ly0 = 0; ly1 = 0; }
+    }
+    tiles_touched[idx] = (o.xmax - o.xmin) * (ly1 - ly0);
     depth_key[idx] = __float_as_uint(o.depth);
-    rect[idx] = make_uint2(o.xmin | (o.xmax << 16), o.ymin | (o.ymax << 16));
+    rect[idx] = make_uint2(o.xmin | (o.xmax << 16), ly0 | (ly1 << 16));
 }
 
 // checkFrustum, rasterizer_impl.cu:54-66
@@ -345,7 +353,7 @@ void launch_preprocess_fwd(const grpg_forward_args* a, float focal_x, float foca
     preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs, a->cov3D_precomp,
         a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos, a->width, a->height, a->tan_fovx, a->tan_fovy,
-        focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped);
+        focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->tile_row_stride, a->tile_row_phase, a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped);
 }
 
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream) {

@@ -109,7 +109,18 @@ typedef struct grpg_forward_args {
     void*  binning_ws;           /* grpg_binning_layout.total_bytes (stage 2 only) */
     void*  image_ws;             /* grpg_image_layout.total_bytes   */
     void*  stream;               /* cudaStream_t */
+    /* Multi-GPU tile-row sharding (no reference counterpart).  With stride k > 1 this call
+     * handles only the tile rows r with r % k == phase: instances are emitted, sorted and blended for
+     * those rows, and out_color/out_depth/out_alpha/out_semantic/n_contrib use the COMPACT band layout
+     * [C, rows_local*16, W] (band row i = tile row i*k + phase).  radii stay global.  stride <= 1 = whole frame. */
+    int tile_row_stride;
+    int tile_row_phase;
 } grpg_forward_args;
+
+/* number of tile rows owned by (stride, phase) for an image of `height` pixels, and the pixel height of
+ * the compact band image (== height when stride <= 1) */
+int grpg_band_rows(int height, int stride, int phase);
+int grpg_band_height(int height, int stride, int phase);
 
 /* Stage 1: projection (preprocessCUDA forward.cu:155-256), depth ordering and the
  * prefix sum of tile counts (rasterizer_impl.cu:280).  Writes R to *num_rendered
@@ -166,8 +177,17 @@ typedef struct grpg_backward_args {
     float* dL_dscale;             /* [P,3] */
     float* dL_drot;               /* [P,4] */
     float* dL_dsemantic;          /* [P,S] or NULL when S==0 */
-    void*  grad_ws;               /* grpg_backward_workspace_bytes(P,S) scratch */
+    void*  grad_ws;               /* [P][12] floats: per-Gaussian 2D gradient record (mean2D xyz, conic xyw, opacity, rgb, depth) */
     void*  stream;
+    int tile_row_stride;          /* band of the forward call whose workspaces are passed (see grpg_forward_args); */
+    int tile_row_phase;           /* alphas and dL_dpix* then use the compact band layout                          */
+    /* stages: 1 = blend backward only (fills grad_ws for all P Gaussians from this band's pixels),
+     *         2 = geometry backward only, for Gaussians [p_begin, p_begin + p_count): grad_ws and every dL_*
+     *             output then hold p_count rows (row i = Gaussian p_begin + i) while the inputs stay full-size,
+     *         3 = both (p_begin = 0, p_count = P).  0 is treated as 3.
+     * Between the stages a multi-GPU caller reduce-scatters grad_ws over the Gaussian axis. */
+    int stages;
+    int p_begin, p_count;
 } grpg_backward_args;
 
 size_t grpg_backward_workspace_bytes(int P, int S);
