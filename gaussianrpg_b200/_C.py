@@ -146,14 +146,14 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                  dL_dout_depth, dL_dout_alpha, dL_dout_semantic, sh, degree, campos, geomBuffer, R,
                                  binningBuffer, imageBuffer, alphas, semantics, debug, *, _band=(1, 0), _height=None,
-                                 _stage=3, _grad_rec=None, _slice=None):
+                                 _width=None, _stage=3, _grad_rec=None, _slice=None):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:126-220).
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
     dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4], dL_dsemantic[P,S]).
 
     Keyword-only extras for the multi-GPU path (gaussianrpg_b200.dist): `_band` as in the forward (the pixel
-    gradients and `alphas` are then band images and `_height` is the frame height); `_stage=1` runs only the
+    gradients and `alphas` are then band images and `_height`/`_width` are the frame size); `_stage=1` runs only the
     blend backward and returns (grad_rec[P,12], dL_dsemantic[P,S]); `_stage=2` runs only the per-Gaussian
     backward for `_slice=(p_begin, p_count)` from `_grad_rec[p_count,12]` and returns p_count-row gradients.
     """
@@ -170,6 +170,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         S = int(semantics.shape[1]) if semantics is not None and semantics.ndim == 2 else 0
     if _height is not None:
         H = int(_height)
+    if _width is not None:
+        W = int(_width)
     M = int(sh.shape[1]) if sh is not None and sh.numel() != 0 else 0
     f32 = dict(dtype=torch.float32, device=dev)
     p_begin, p_count = (0, P) if _slice is None else (int(_slice[0]), int(_slice[1]))

@@ -19,7 +19,7 @@ namespace grpg {
 // ---- 2. exclusive scan of tiles_touched in sorted order (decoupled look-back) ------------
 constexpr int SCAN_IPT = 8;
 constexpr int SCAN_TILE = 256 * SCAN_IPT;
-constexpr uint32_t EMIT_CHUNK = 4096;                      // instances emitted per warp
+constexpr uint32_t EMIT_CHUNK = 1024;                      // instances emitted per warp
 constexpr uint32_t EMIT_MAX_CHUNKS = (1u << 30) / EMIT_CHUNK + 2;  // R < 2^30 is enforced by the API
 constexpr unsigned long long SC_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long SC_FLAG_PREFIX = 2ull << 62;
@@ -27,11 +27,11 @@ constexpr unsigned long long SC_FLAG_MASK = 3ull << 62;
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restrict__ sorted_idx,
@@ -152,15 +152,26 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __r
 // ---- 5. tile ranges (identifyTileRanges, rasterizer_impl.cu:116-138) -----------------------
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ tile_keys, uint32_t R,
                                                           uint2* __restrict__ ranges) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t cur = tile_keys[i];
-    if (i == 0) ranges[cur].x = 0;
-    else {
-        const uint32_t prev = tile_keys[i - 1];
-        if (cur != prev) { ranges[prev].y = i; ranges[cur].x = i; }
+    // 4 keys per thread (one 16-byte load) + the key before them
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= R) return;
+    uint32_t k[4];
+    int n = 4;
+    if (i0 + 4 <= R) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tile_keys + i0);
+        k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+    } else {
+        n = (int)(R - i0);
+        for (int j = 0; j < n; ++j) k[j] = tile_keys[i0 + j];
     }
-    if (i == R - 1) ranges[cur].y = R;
+    uint32_t prev = i0 == 0 ? 0xFFFFFFFFu : tile_keys[i0 - 1];
+    for (int j = 0; j < n; ++j) {
+        const uint32_t i = i0 + j, cur = k[j];
+        if (i == 0) ranges[cur].x = 0;
+        else if (cur != prev) { ranges[prev].y = i; ranges[cur].x = i; }
+        if (i == R - 1) ranges[cur].y = R;
+        prev = cur;
+    }
 }
 
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ out, uint32_t n) {
@@ -211,12 +222,9 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
     p += 256;
     uint32_t* chunk_start = (uint32_t*)p;
 
-    {
-        ProfScope ps("iota", stream);
-        iota_kernel<<<(P + 255) / 256, 256, 0, stream>>>(sorted_idx, (uint32_t)P);
-    }
+    // values start as the identity permutation: generated inside the first digit pass, no iota kernel
     bool in_a = onesweep_sort_pairs(depth_key, sorted_idx, keys_b, vals_b, P, 32, aux, num_sms, stream,
-                                    "depth_sort_hist", "depth_sort_pass");
+                                    "depth_sort_hist", "depth_sort_pass", /*iota_values=*/true);
     if (!in_a) {  // 32 bits -> 4 passes -> always lands back in the a-buffers; kept for safety
         cudaMemcpyAsync(depth_key, keys_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(sorted_idx, vals_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
@@ -260,7 +268,7 @@ void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tile
     }
     onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream, "tile_sort_hist", "tile_sort_pass");
     ProfScope ps("tile_ranges", stream);
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(tile_keys, (uint32_t)R, ranges);
+    tile_ranges_kernel<<<(unsigned)((R + 1023) / 1024), 256, 0, stream>>>(tile_keys, (uint32_t)R, ranges);
 }
 
 void launch_reference_keys(long long R, const uint32_t* point_list, const uint32_t* tile_keys, const Rec* rec,

@@ -137,8 +137,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
             const int j = g0 + lane;
             bool hit = false;
             if (j < cnt) {
-                const float4 a = s_a[j];
-                hit = (a.x + a.z >= bx_lo) && (a.x - a.z <= bx_hi) && (a.y + a.w >= by_lo) && (a.y - a.w <= by_hi);
+                hit = footprint_hits(s_a[j], bx_lo, bx_hi, by_lo, by_hi);
             }
             uint32_t m = __ballot_sync(0xffffffffu, hit);
             while (m) {
@@ -150,9 +149,11 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                 const uint32_t gid = s_id[k];
                 const float dx = a.x - pxf, dy = a.y - pyf;
                 const float power = ffma(ffma(dx, fmul(dx, b.x), fmul(dy, fmul(dy, b.z))), -0.5f, -fmul(dy, fmul(dx, b.y)));
+                const bool maybe = (pos < last_contributor) && !(power > 0.0f) && !(power < a.w);
+                if (!__any_sync(0xffffffffu, maybe)) continue;  // exact-ellipse vote, see blend_fwd.cu
                 const float G = expf(power);
                 const float alpha = fminf(0.99f, b.w * G);
-                const bool active = (pos < last_contributor) && !(power > 0.0f) && (alpha >= 1.0f / 255.0f);
+                const bool active = maybe && (alpha >= 1.0f / 255.0f);
                 if (!__any_sync(0xffffffffu, active)) continue;
 
                 float g_mx = 0.f, g_my = 0.f, g_mabs = 0.f, g_cx = 0.f, g_cy = 0.f, g_cw = 0.f, g_op = 0.f;

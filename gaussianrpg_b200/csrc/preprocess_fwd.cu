@@ -203,9 +203,11 @@ __device__ __forceinline__ uint32_t sh_to_rgb(int deg, const float* __restrict__
 // conic/opacity (the quantities the blend evaluates).  Used only to skip work whose result
 // the reference would discard (forward.cu:418-426), never to change a result.
 __device__ __forceinline__ void alpha_footprint(float A, float B, float C, float opacity, int radius, float& hx,
-                                                float& hy) {
+                                                float& hy, float& thr) {
     const float inf = __int_as_float(0x7f800000);
     hx = inf; hy = inf;
+    thr = -inf;  // `power < thr` must imply min(0.99, o*expf(power)) < 1/255 (expf is accurate to 2 ulp)
+    if (opacity > 0.0f && opacity < inf) thr = __double2float_rd(log(1.0 / (255.0 * (double)opacity)) - 1e-4);
     if (!(opacity >= 0.0f) || !isfinite(A) || !isfinite(B) || !isfinite(C)) return;  // keep exact behaviour for odd inputs
     if (opacity < 1.0f / 255.0f) { hx = -inf; hy = -inf; return; }  // alpha = o*G <= o < 1/255 always
     const double dA = A, dB = B, dC = C;
@@ -283,10 +285,10 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
         clamped[idx] = (uint8_t)cmask;
     }
     const float opacity = opacities[idx];
-    float hx, hy;
-    alpha_footprint(o.conx, o.cony, o.conz, opacity, o.radius, hx, hy);
+    float hx, hy, thr;
+    alpha_footprint(o.conx, o.cony, o.conz, opacity, o.radius, hx, hy, thr);
     Rec r;
-    r.a = make_float4(o.px, o.py, hx, hy);
+    r.a = make_float4(o.px, o.py, pack_extents(hx, hy), thr);
     r.b = make_float4(o.conx, o.cony, o.conz, opacity);
     r.c = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
     rec[idx] = r;

@@ -72,11 +72,11 @@ __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __r
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // exclusive scan of one value per thread across a 256-thread block
@@ -103,11 +103,11 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 // ---- one onesweep digit pass -----------------------------------------------------------
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
+__global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift, int bits,
     const uint32_t* __restrict__ hist /*[256] for this pass*/, uint32_t* __restrict__ tile_counter,
-    uint32_t* __restrict__ lookback /*[tiles][256]*/) {
+    uint32_t* __restrict__ lookback /*[tiles][256]*/, int iota_values) {
     __shared__ uint32_t s_warp_hist[8][256];
     __shared__ uint32_t s_local_start[256];
     __shared__ uint32_t s_bin_base[256];
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
         uint32_t d = (key[i] >> shift) & mask;
         uint32_t p = s_local_start[d] + s_warp_hist[warp][d] + rank[i];
         s_keys[p] = key[i];
-        s_vals[p] = idx < n ? vals_in[idx] : 0u;
+        s_vals[p] = idx < n ? (iota_values ? idx : vals_in[idx]) : 0u;
     }
     __syncthreads();
     // coalesced-by-run write-out: slot p of the tile goes to s_bin_base[digit] + p
@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(
 // cleared here.
 static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                                        long long n, int total_bits, uint32_t* aux, int num_sms, cudaStream_t stream,
-                                       const char* hist_name = "sort_hist", const char* pass_name = "sort_pass") {
+                                       const char* hist_name = "sort_hist", const char* pass_name = "sort_pass",
+                                       bool iota_values = false) {
     if (n <= 0) return true;
     SortPlan plan = make_sort_plan(total_bits);
     size_t tiles = sort_num_tiles(n);
@@ -235,7 +236,7 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
         ProfScope ps(pass_name, stream);
         onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
             ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p,
-            lookback + (size_t)p * tiles * 256);
+            lookback + (size_t)p * tiles * 256, (iota_values && p == 0) ? 1 : 0);
         in_a = !in_a;
     }
     return in_a;

@@ -29,7 +29,7 @@ def parse_buffers(P: int, R: int, W: int, H: int, geom: torch.Tensor, binning: t
     rec = _view(geom, gl.rec, P * 12, torch.float32).view(P, 3, 4)
     rect = _view(geom, gl.rect, P * 2, torch.int32).view(P, 2)
     out = dict(
-        means2D=rec[:, 0, 0:2], footprint=rec[:, 0, 2:4], conic_opacity=rec[:, 1, :], rgb=rec[:, 2, 0:3],
+        means2D=rec[:, 0, 0:2], conic_opacity=rec[:, 1, :], rgb=rec[:, 2, 0:3],
         depths=rec[:, 2, 3], tiles_touched=_view(geom, gl.tiles_touched, P, torch.int32),
         cov3D=_view(geom, gl.cov3d, P * 6, torch.float32).view(P, 6), clamped=_view(geom, gl.clamped, P, torch.uint8),
         sorted_idx=_view(geom, gl.sorted_idx, P, torch.int32), offsets=_view(geom, gl.offsets, P, torch.int32),

@@ -148,7 +148,7 @@ class _ShardedRasterize(torch.autograd.Function):
         tail = (sh, rs.sh_degree, rs.campos, geom, ctx.R, binning, img, alpha_b, semantics, rs.debug)
         grad_rec, g_semantics = _C.rasterize_gaussians_backward(
             *common, gb[:3].contiguous(), gb[3:4].contiguous(), gb[4:5].contiguous(), gb[5:5 + S].contiguous(), *tail,
-            _band=(k, r), _height=H, _stage=1)
+            _band=(k, r), _height=H, _width=W, _stage=1)
         # reduce-scatter the per-Gaussian 2D gradient records over the Gaussian axis
         Pp = padded_count(P, k)
         if Pp != P:
@@ -156,7 +156,7 @@ class _ShardedRasterize(torch.autograd.Function):
         mine = _reduce_scatter_rows(grad_rec, group, k, r)
         p_begin, p_count = gaussian_slice(P, k, r)
         shard = _C.rasterize_gaussians_backward(
-            *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _stage=2,
+            *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _width=W, _stage=2,
             _grad_rec=mine[:max(p_count, 1)], _slice=(p_begin, p_count))
         per = Pp // k
         full = []
