@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     __shared__ float4 s_c[BWD_BATCH];
     __shared__ uint32_t s_id[BWD_BATCH];
     __shared__ int s_maxlast[8];
+    __shared__ uint8_t s_q[8][BWD_BATCH];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
@@ -133,16 +134,21 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
         __syncthreads();
         if (wmax <= top - cnt) continue;  // every pixel of this warp ended before this batch
 
+        // phase 1: footprint test of the whole batch, survivors compacted into a per-warp byte queue
+        uint8_t* q = s_q[warp];
+        int n_q = 0;
         for (int g0 = 0; g0 < cnt; g0 += 32) {
             const int j = g0 + lane;
-            bool hit = false;
-            if (j < cnt) {
-                hit = footprint_hits(s_a[j], bx_lo, bx_hi, by_lo, by_hi);
-            }
-            uint32_t m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int k = g0 + __ffs(m) - 1;
-                m &= m - 1;
+            const bool hit = j < cnt && footprint_hits(s_a[j], bx_lo, bx_hi, by_lo, by_hi);
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
+            n_q += __popc(m);
+        }
+        __syncwarp();
+        // phase 2: back-to-front replay of the survivors
+        {
+            for (int qi = 0; qi < n_q; ++qi) {
+                const int k = q[qi];
                 const int pos = top - 1 - k;  // 0-based position in the tile's range
                 const float4 a = s_a[k];
                 const float4 b = s_b[k];
@@ -170,7 +176,8 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                     for (int i = 0; i < SB; ++i) sv[i] = i < S ? __ldg(sp + i) : 0.f;
                 }
                 if (active) {
-                    T = T / (1.f - alpha);
+                    const float inv_1ma = __frcp_rn(1.f - alpha);  // one reciprocal serves T/(1-a) and T_final/(1-a)
+                    T = T * inv_1ma;
                     const float w_at = alpha * T;
                     float dL_dopa = 0.f;
                     acc0 = last_alpha * lastc0 + (1.f - last_alpha) * acc0; lastc0 = c.x;
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                     dL_dopa += (1.f - acc_alpha) * dpix_alpha;
                     dL_dopa *= T;
                     last_alpha = alpha;
-                    dL_dopa += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                    dL_dopa += (-T_final * inv_1ma) * bg_dot_dpixel;
 
                     const float dL_dG = b.w * dL_dopa;
                     const float gdx = G * dx, gdy = G * dy;
