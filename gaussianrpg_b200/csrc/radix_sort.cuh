@@ -126,12 +126,18 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
     const uint32_t tile_base = tile * SORT_TILE;
     const uint32_t warp_base = tile_base + warp * (32 * SORT_IPT);
 
-    uint32_t key[SORT_IPT];
+    uint32_t key[SORT_IPT], val[SORT_IPT];
     uint16_t rank[SORT_IPT];
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
         uint32_t idx = warp_base + i * 32 + lane;
         key[i] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
+    }
+    // values are requested now so that their latency hides behind the ranking
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; ++i) {
+        uint32_t idx = warp_base + i * 32 + lane;
+        val[i] = idx < n ? (iota_values ? idx : vals_in[idx]) : 0u;
     }
     const uint32_t lt_mask = (1u << lane) - 1u;
     // Stable multi-split ranking.  `match.any` runs on the slow ADU pipe on sm_100 (measured: 57 % ADU
@@ -175,14 +181,22 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
     // decoupled look-back over preceding tiles for digit `tid`
     uint32_t excl = 0;
     if (tile > 0) {
+        // windowed look-back: fetch up to 4 predecessor states per round trip instead of one
         int t = (int)tile - 1;
-        while (true) {
-            uint32_t v = ld_volatile_u32(lookback + (size_t)t * 256 + tid);
-            uint32_t f = v & LB_FLAG_MASK;
-            if (f == 0) continue;  // not published yet
-            excl += v & LB_VALUE_MASK;
-            if (f == LB_FLAG_PREFIX) break;
-            --t;  // t >= 0 always terminates at tile 0, which publishes PREFIX
+        bool found = false;
+        while (!found) {
+            uint32_t v[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) v[w] = (t - w >= 0) ? ld_volatile_u32(lookback + (size_t)(t - w) * 256 + tid) : LB_FLAG_PREFIX;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (found) break;
+                uint32_t x = v[w];
+                while ((x & LB_FLAG_MASK) == 0) x = ld_volatile_u32(lookback + (size_t)(t - w) * 256 + tid);
+                excl += x & LB_VALUE_MASK;
+                if ((x & LB_FLAG_MASK) == LB_FLAG_PREFIX) found = true;
+            }
+            t -= 4;
         }
         st_volatile_u32(my_lb, (excl + total) | LB_FLAG_PREFIX);
     }
@@ -193,11 +207,10 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
     // scatter keys and values into tile-sorted order in shared memory
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
-        uint32_t idx = warp_base + i * 32 + lane;
         uint32_t d = (key[i] >> shift) & mask;
         uint32_t p = s_local_start[d] + s_warp_hist[warp][d] + rank[i];
         s_keys[p] = key[i];
-        s_vals[p] = idx < n ? (iota_values ? idx : vals_in[idx]) : 0u;
+        s_vals[p] = val[i];
     }
     __syncthreads();
     // coalesced-by-run write-out: slot p of the tile goes to s_bin_base[digit] + p
