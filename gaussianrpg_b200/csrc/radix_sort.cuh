@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift, int bits,
     const uint32_t* __restrict__ hist /*[256] for this pass*/, uint32_t* __restrict__ tile_counter,
-    uint32_t* __restrict__ lookback /*[tiles][256]*/, int iota_values) {
+    uint32_t* __restrict__ lookback /*[tiles][256]*/, int iota_values, int precomputed_offsets) {
     __shared__ uint32_t s_warp_hist[8][256];
     __shared__ uint32_t s_local_start[256];
     __shared__ uint32_t s_bin_base[256];
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mask = (1u << bits) - 1u;
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    // look-back mode needs tile ids in scheduling order; with precomputed offsets the block index will do
+    if (tid == 0) s_tile = precomputed_offsets ? blockIdx.x : atomicAdd(tile_counter, 1u);
 #pragma unroll
     for (int w = 0; w < 8; ++w) s_warp_hist[w][tid] = 0;
     __syncthreads();
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
     }
     // publish the tile aggregate as early as possible
     uint32_t* my_lb = lookback + (size_t)tile * 256 + tid;
-    st_volatile_u32(my_lb, total | (tile == 0 ? LB_FLAG_PREFIX : LB_FLAG_AGG));
+    if (!precomputed_offsets) st_volatile_u32(my_lb, total | (tile == 0 ? LB_FLAG_PREFIX : LB_FLAG_AGG));
 
     uint32_t local_start = block_exclusive_scan_256(total, s_scan);
     uint32_t ghist = hist[tid];
@@ -180,7 +181,9 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
 
     // decoupled look-back over preceding tiles for digit `tid`
     uint32_t excl = 0;
-    if (tile > 0) {
+    if (precomputed_offsets) {
+        excl = *my_lb;  // exclusive count of this digit in all earlier tiles (radix_tile_scan_kernel)
+    } else if (tile > 0) {
         // windowed look-back: fetch up to 4 predecessor states per round trip instead of one
         int t = (int)tile - 1;
         bool found = false;
@@ -227,6 +230,54 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
     }
 }
 
+// ---- split pass (no look-back): per-tile digit histograms, a scan over tiles per digit, then the scatter ------
+// For the sizes of this path (2 M Gaussians -> 488 tiles, ~15 M instances -> ~3.6 k tiles) every tile of a
+// onesweep pass is resident at once and the decoupled look-back degenerates into a serial prefix chain
+// (measured: 30 us per pass at 2 M keys, 22 % of stall samples on the look-back load).  Reading the keys a second
+// time (4 B per pair) to precompute the offsets is cheaper.
+__global__ void __launch_bounds__(SORT_THREADS) radix_tile_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+                                                                      int shift, int bits,
+                                                                      uint32_t* __restrict__ tile_hist /*[tiles][256]*/) {
+    __shared__ uint32_t s_hist[256];
+    const int tid = threadIdx.x;
+    s_hist[tid] = 0;
+    __syncthreads();
+    const uint32_t mask = (1u << bits) - 1u;
+    const uint32_t base = blockIdx.x * SORT_TILE;
+#pragma unroll
+    for (int i = 0; i < SORT_IPT / 4; ++i) {
+        const uint32_t idx = base + (i * SORT_THREADS + tid) * 4;
+        if (idx + 4 <= n) {
+            const uint4 v = *reinterpret_cast<const uint4*>(keys + idx);
+            atomicAdd(&s_hist[(v.x >> shift) & mask], 1u);
+            atomicAdd(&s_hist[(v.y >> shift) & mask], 1u);
+            atomicAdd(&s_hist[(v.z >> shift) & mask], 1u);
+            atomicAdd(&s_hist[(v.w >> shift) & mask], 1u);
+        } else {
+            for (uint32_t j = idx; j < n && j < idx + 4; ++j) atomicAdd(&s_hist[(keys[j] >> shift) & mask], 1u);
+        }
+    }
+    __syncthreads();
+    tile_hist[(size_t)blockIdx.x * 256 + tid] = s_hist[tid];
+}
+
+// one CTA per digit: exclusive scan of that digit's counts over the tiles (in place) + the digit total
+__global__ void __launch_bounds__(256) radix_tile_scan_kernel(uint32_t* __restrict__ tile_hist, uint32_t tiles,
+                                                              uint32_t* __restrict__ digit_totals /*[256]*/) {
+    __shared__ uint32_t s_scan[8];
+    const uint32_t d = blockIdx.x;
+    uint32_t running = 0;
+    for (uint32_t t0 = 0; t0 < tiles; t0 += 256) {
+        const uint32_t t = t0 + threadIdx.x;
+        const uint32_t v = t < tiles ? tile_hist[(size_t)t * 256 + d] : 0u;
+        uint32_t chunk_total;
+        const uint32_t ex = block_exclusive_scan_256(v, s_scan, &chunk_total);
+        if (t < tiles) tile_hist[(size_t)t * 256 + d] = running + ex;
+        running += chunk_total;
+    }
+    if (threadIdx.x == 0) digit_totals[d] = running;
+}
+
 // Sorts n pairs on bits [0, total_bits).  Input in (keys_a, vals_a); (keys_b, vals_b) is the
 // ping-pong partner.  Returns true when the sorted result ends in the *_a buffers, false for *_b.
 // `aux` must hold SORT_MAX_PASSES*(256+64) uint32 + SORT_MAX_PASSES*tiles*256 uint32 and is
@@ -241,25 +292,24 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
     uint32_t* hist = aux;                                  // [4][256]
     uint32_t* counters = aux + SORT_MAX_PASSES * 256;      // [4] (padded to 64 words)
     uint32_t* lookback = aux + SORT_MAX_PASSES * (256 + 64);
-    size_t clear_words = (size_t)SORT_MAX_PASSES * (256 + 64) + (size_t)plan.passes * tiles * 256;
-    cudaMemsetAsync(aux, 0, clear_words * sizeof(uint32_t), stream);
-    int hgrid = (int)((n + 256 * 4 * 8 - 1) / (256 * 4 * 8));
-    if (hgrid > num_sms * 8) hgrid = num_sms * 8;
-    if (hgrid < 1) hgrid = 1;
-    {
-        ProfScope ps(hist_name, stream);
-        sort_histogram_kernel<<<hgrid, 256, 0, stream>>>(keys_a, (uint32_t)n, plan, hist);
-    }
+    (void)num_sms;
     bool in_a = true;
     for (int p = 0; p < plan.passes; ++p) {
         const uint32_t* ki = in_a ? keys_a : keys_b;
         const uint32_t* vi = in_a ? vals_a : vals_b;
         uint32_t* ko = in_a ? keys_b : keys_a;
         uint32_t* vo = in_a ? vals_b : vals_a;
+        uint32_t* tile_offsets = lookback + (size_t)p * tiles * 256;
+        {
+            ProfScope ps(hist_name, stream);
+            radix_tile_hist_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(ki, (uint32_t)n, plan.shift[p],
+                                                                                plan.bits[p], tile_offsets);
+            radix_tile_scan_kernel<<<256, 256, 0, stream>>>(tile_offsets, (uint32_t)tiles, hist + p * 256);
+        }
         ProfScope ps(pass_name, stream);
         onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
-            ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p,
-            lookback + (size_t)p * tiles * 256, (iota_values && p == 0) ? 1 : 0);
+            ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
+            (iota_values && p == 0) ? 1 : 0, /*precomputed_offsets=*/1);
         in_a = !in_a;
     }
     return in_a;

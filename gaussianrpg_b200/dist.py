@@ -105,6 +105,9 @@ def _all_gather_rows(x: torch.Tensor, group, k: int) -> torch.Tensor:
     return out
 
 
+_EXCHANGE_PLAN = "replicate"  # or "shard"; see _ShardedRasterize.backward
+
+
 # ---- the sharded operator --------------------------------------------------------------------------
 class _ShardedRasterize(torch.autograd.Function):
     @staticmethod
@@ -149,24 +152,37 @@ class _ShardedRasterize(torch.autograd.Function):
         grad_rec, g_semantics = _C.rasterize_gaussians_backward(
             *common, gb[:3].contiguous(), gb[3:4].contiguous(), gb[4:5].contiguous(), gb[5:5 + S].contiguous(), *tail,
             _band=(k, r), _height=H, _width=W, _stage=1)
-        # reduce-scatter the per-Gaussian 2D gradient records over the Gaussian axis
-        Pp = padded_count(P, k)
-        if Pp != P:
-            grad_rec = torch.nn.functional.pad(grad_rec, (0, 0, 0, Pp - P))
-        mine = _reduce_scatter_rows(grad_rec, group, k, r)
-        p_begin, p_count = gaussian_slice(P, k, r)
-        shard = _C.rasterize_gaussians_backward(
-            *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _width=W, _stage=2,
-            _grad_rec=mine[:max(p_count, 1)], _slice=(p_begin, p_count))
-        per = Pp // k
-        full = []
-        for t in shard[:8]:  # means2D, colors, opacity, means3D, cov3D, sh, scales, rot
-            flat = t.reshape(t.shape[0], -1)
-            if flat.shape[0] != per:
-                flat = torch.nn.functional.pad(flat, (0, 0, 0, per - flat.shape[0]))
-            g = _all_gather_rows(flat, group, k)[:P]
-            full.append(g.reshape((P,) + tuple(t.shape[1:])))
-        g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = full
+        # Sum the per-Gaussian 2D gradient records over ranks.  Two exchange plans:
+        #  "shard":     reduce-scatter the 48 B records, per-Gaussian backward on the owned slice, all-gather the
+        #               parameter-gradient shards (104 B per Gaussian for means/sh/opacity/scale/rotation);
+        #  "replicate": reduce-scatter + all-gather of the 48 B records themselves (= all-reduce), then every rank
+        #               runs the (cheap, 0.15 ms at 2 M) per-Gaussian backward for all Gaussians.
+        # "replicate" moves less than half the bytes and is the default; "shard" is what a ZeRO-style sharded
+        # optimiser would use (it would simply skip the final all-gather).
+        if _EXCHANGE_PLAN == "replicate":
+            dist.all_reduce(grad_rec, op=dist.ReduceOp.SUM, group=group)
+            shard = _C.rasterize_gaussians_backward(
+                *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _width=W, _stage=2,
+                _grad_rec=grad_rec, _slice=(0, P))
+            g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = shard[:8]
+        else:
+            Pp = padded_count(P, k)
+            if Pp != P:
+                grad_rec = torch.nn.functional.pad(grad_rec, (0, 0, 0, Pp - P))
+            mine = _reduce_scatter_rows(grad_rec, group, k, r)
+            p_begin, p_count = gaussian_slice(P, k, r)
+            shard = _C.rasterize_gaussians_backward(
+                *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _width=W, _stage=2,
+                _grad_rec=mine[:max(p_count, 1)], _slice=(p_begin, p_count))
+            per = Pp // k
+            full = []
+            for t in shard[:8]:  # means2D, colors, opacity, means3D, cov3D, sh, scales, rot
+                flat = t.reshape(t.shape[0], -1)
+                if flat.shape[0] != per:
+                    flat = torch.nn.functional.pad(flat, (0, 0, 0, per - flat.shape[0]))
+                g = _all_gather_rows(flat, group, k)[:P]
+                full.append(g.reshape((P,) + tuple(t.shape[1:])))
+            g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = full
         if S > 0:
             dist.all_reduce(g_semantics, op=dist.ReduceOp.SUM, group=group)
         grads = (g_means3D, g_means2D, g_sh, g_colors, g_semantics, g_opac, g_scales, g_rot, g_cov3D)
@@ -277,7 +293,7 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
         "gpu_launches": 16 * args.steps,
         "config": {"workload": f"street scene {P} Gaussians, {W}x{H}, fwd+bwd, one frame split over {world} GPUs",
                    "parallelism": f"tile rows interleaved mod {world} (fwd, all-gather {band_bytes} B/rank) + "
-                                  f"Gaussian-axis reduce-scatter of 48 B records (bwd, {48 * P} B) + all-gather of "
-                                  f"parameter-gradient shards",
+                                  f"all-reduce (reduce-scatter + all-gather) of the 48 B per-Gaussian gradient records "
+                                  f"(bwd, {48 * P} B), per-Gaussian backward replicated",
                    "l2": "no flush: one step streams > 126 MB per GPU"},
     }
