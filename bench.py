@@ -275,6 +275,13 @@ def main():
                                          False, False)
     R, V = int(raw[0]), int((raw[5] > 0).sum())
     P = sc.means3D.shape[0]
+    if args.impl == "ours":  # self-check of the index structures behind the timed numbers
+        from gaussianrpg_b200 import debug as _dbg
+        _p = _dbg.parse_buffers(P, R, W, H, raw[6], raw[7], raw[8])
+        _perm = bool((_p["sorted_idx"].long().sort().values == torch.arange(P, device=dev)).all())
+        _sum = int(_p["tiles_touched"].long().sum())
+        base["index_check"] = {"R": R, "sum_tiles_touched": _sum, "depth_order_is_permutation": _perm,
+                               "keys_sorted": bool((_p["point_list_keys"][1:] >= _p["point_list_keys"][:-1]).all())}
 
     result = dict(base)
     result.update(

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
         for (int g0 = 0; g0 < cnt; g0 += 32) {
             const int j = g0 + lane;
             // slots whose position lies behind every pixel's last contributor cannot receive gradient
-            const bool hit = j < cnt && (top - 1 - j) < wmax && footprint_hits(s_a[j], bx_lo, bx_hi, by_lo, by_hi);
+            const bool hit = j < cnt && (top - 1 - j) < wmax && footprint_hits_exact(s_a[j], s_b[j], bx_lo, bx_hi, by_lo, by_hi);
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
             if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
             n_q += __popc(m);

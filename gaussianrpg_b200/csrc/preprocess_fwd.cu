@@ -205,20 +205,23 @@ __device__ __forceinline__ uint32_t sh_to_rgb(int deg, const float* __restrict__
 __device__ __forceinline__ void alpha_footprint(float A, float B, float C, float opacity, int radius, float& hx,
                                                 float& hy, float& thr) {
     const float inf = __int_as_float(0x7f800000);
-    hx = inf; hy = inf;
-    thr = -inf;  // `power < thr` must imply min(0.99, o*expf(power)) < 1/255 (expf is accurate to 2 ulp)
-    if (opacity > 0.0f && opacity < inf) thr = __double2float_rd(log(1.0 / (255.0 * (double)opacity)) - 1e-4);
+    hx = inf; hy = inf; thr = -inf;
     if (!(opacity >= 0.0f) || !isfinite(A) || !isfinite(B) || !isfinite(C)) return;  // keep exact behaviour for odd inputs
-    if (opacity < 1.0f / 255.0f) { hx = -inf; hy = -inf; return; }  // alpha = o*G <= o < 1/255 always
+    if (opacity < 1.0f / 255.0f) { hx = -inf; hy = -inf; thr = inf; return; }  // alpha = o*G <= o < 1/255 always
     const double dA = A, dB = B, dC = C;
-    const double D = dA * dC - dB * dB;
-    if (!(D > 0.0) || !(dA > 0.0) || !(dC > 0.0)) return;  // not an ellipse: no culling
-    // alpha >= 1/255  <=>  A dx^2 + 2B dx dy + C dy^2 <= 2 ln(255 o) =: tau
-    double tau = 2.0 * log(255.0 * (double)opacity);
-    // slack for the float evaluation of `power` (three products, two sums) at |d| <= radius + 16
+    // Worst-case error of the float evaluation of `power` (three products, two sums) anywhere in a tile the
+    // Gaussian is binned to (|d| <= radius + 16): the blend may only skip a pixel when even that error cannot lift
+    // alpha over 1/255.
     const double dmax = (double)radius + 17.0;
-    tau += 8.0 * 1.1920929e-7 * (fabs(dA) + fabs(dC) + 2.0 * fabs(dB)) * dmax * dmax + 1e-4;
-    tau *= 1.0 + 1e-5;
+    const double slack_q = 8.0 * 1.1920929e-7 * (fabs(dA) + fabs(dC) + 2.0 * fabs(dB)) * dmax * dmax + 1e-4;
+    // `power < thr` must imply min(0.99, o*expf(power)) < 1/255 (expf is accurate to 2 ulp); thr also serves as
+    // the geometric bound q = A dx^2 + 2B dx dy + C dy^2 > -2 thr of the phase-1 ellipse test, hence the slack
+    const double lthr = log(1.0 / (255.0 * (double)opacity)) - 1e-4 - 0.5 * slack_q;
+    thr = __double2float_rd(lthr);
+    const double D = dA * dC - dB * dB;
+    if (!(D > 0.0) || !(dA > 0.0) || !(dC > 0.0)) return;  // not an ellipse: no bounding box
+    // alpha >= 1/255  <=>  q <= 2 ln(255 o) =: tau
+    double tau = (-2.0 * lthr) * (1.0 + 1e-5);
     if (tau <= 0.0) { hx = -inf; hy = -inf; return; }
     const double ex = sqrt(tau * dC / D) + 1e-2;
     const double ey = sqrt(tau * dA / D) + 1e-2;
