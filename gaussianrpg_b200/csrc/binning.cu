@@ -58,23 +58,34 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
     }
     uint32_t block_total;
     uint32_t texcl = block_exclusive_scan_256(sum, s_scan, &block_total);
-    if (threadIdx.x == 0) {
-        st_volatile_u64(status + tile, (unsigned long long)block_total | (tile == 0 ? SC_FLAG_PREFIX : SC_FLAG_AGG));
+    // warp-parallel decoupled look-back: all ~1000 tiles of a 2 M-Gaussian scan are resident at once, so a
+    // one-predecessor-per-step walk would be a serial chain; warp 0 inspects 32 predecessors per step instead
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        if (lane == 0)
+            st_volatile_u64(status + tile, (unsigned long long)block_total | (tile == 0 ? SC_FLAG_PREFIX : SC_FLAG_AGG));
         unsigned long long excl = 0;
-        if (tile > 0) {
-            int t = (int)tile - 1;
-            while (true) {
-                unsigned long long s = ld_volatile_u64(status + t);
-                unsigned long long f = s & SC_FLAG_MASK;
-                if (f == 0) continue;
-                excl += s & ~SC_FLAG_MASK;
-                if (f == SC_FLAG_PREFIX) break;
-                --t;
+        int t = (int)tile - 1;
+        while (t >= 0) {
+            const int idx = t - lane;
+            unsigned long long sv = idx >= 0 ? ld_volatile_u64(status + idx) : SC_FLAG_PREFIX;  // before tile 0: prefix 0
+            while (__any_sync(0xffffffffu, (sv & SC_FLAG_MASK) == 0)) {
+                if ((sv & SC_FLAG_MASK) == 0) sv = ld_volatile_u64(status + idx);
             }
-            st_volatile_u64(status + tile, (excl + block_total) | SC_FLAG_PREFIX);
+            const uint32_t pm = __ballot_sync(0xffffffffu, (sv & SC_FLAG_MASK) == SC_FLAG_PREFIX);
+            const int first = pm ? __ffs(pm) - 1 : 32;  // nearest predecessor that already holds a full prefix
+            uint32_t v = lane <= first ? (uint32_t)(sv & ~SC_FLAG_MASK) : 0u;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            excl += v;
+            if (pm) break;
+            t -= 32;
         }
-        s_excl = excl;
-        if ((tile + 1) * (unsigned long long)SCAN_TILE >= P) *total_out = excl + block_total;
+        if (lane == 0) {
+            if (tile > 0) st_volatile_u64(status + tile, (excl + block_total) | SC_FLAG_PREFIX);
+            s_excl = excl;
+            if ((tile + 1) * (unsigned long long)SCAN_TILE >= P) *total_out = excl + block_total;
+        }
     }
     __syncthreads();
     uint32_t run = (uint32_t)s_excl + texcl;

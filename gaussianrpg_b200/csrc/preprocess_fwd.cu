@@ -239,16 +239,45 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     uint2* __restrict__ rect, uint32_t* __restrict__ tiles_touched, float* __restrict__ cov3D_out,
     uint8_t* __restrict__ clamped) {
     __shared__ float s_cam[35];
+    // Per-CTA slices of the AoS attribute arrays are contiguous in global memory (256 x 12 B means, 256 x 12 B
+    // scales, 256 x 48 B SH at M = 4), so they are staged with TMA bulk copies (one elected thread, one mbarrier)
+    // and then read conflict-free from shared memory -- instead of 12-byte-strided per-thread loads.
+    __shared__ __align__(16) float s_means[256 * 3];
+    __shared__ __align__(16) float s_scales[256 * 3];
+    __shared__ __align__(16) float s_sh[256 * 12];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int cta_first = blockIdx.x * blockDim.x;
+    auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    // the ragged last CTA and 16-byte-misaligned views use plain loads
+    const bool full_cta = cta_first + 256 <= P && aligned16(means3D);
+    const bool stage_scales = full_cta && scales != nullptr && cov3D_precomp == nullptr && aligned16(scales);
+    const bool stage_sh = full_cta && shs != nullptr && colors_precomp == nullptr && M == 4 && aligned16(shs);
+    if (full_cta) {
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t bytes = 256 * 12;
+            if (stage_scales) bytes += 256 * 12;
+            if (stage_sh) bytes += 256 * 48;
+            mbar_expect_tx(&s_bar, bytes);
+            tma_bulk_g2s(s_means, means3D + 3 * (size_t)cta_first, 256 * 12, &s_bar);
+            if (stage_scales) tma_bulk_g2s(s_scales, scales + 3 * (size_t)cta_first, 256 * 12, &s_bar);
+            if (stage_sh) tma_bulk_g2s(s_sh, shs + 12 * (size_t)cta_first, 256 * 48, &s_bar);
+        }
+    }
     if (threadIdx.x < 16) s_cam[threadIdx.x] = viewmatrix[threadIdx.x];
     else if (threadIdx.x < 32) s_cam[threadIdx.x] = projmatrix[threadIdx.x - 16];
     else if (threadIdx.x < 35) s_cam[threadIdx.x] = cam_pos[threadIdx.x - 32];
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (full_cta) mbar_wait(&s_bar, 0);
     if (idx >= P) return;
     const float* v = s_cam;
     const float* m = s_cam + 16;
 
-    const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    float x, y, z;
+    if (full_cta) { x = s_means[3 * threadIdx.x]; y = s_means[3 * threadIdx.x + 1]; z = s_means[3 * threadIdx.x + 2]; }
+    else { x = means3D[3 * idx]; y = means3D[3 * idx + 1]; z = means3D[3 * idx + 2]; }
     float cov3D[6];
     ProjOut o;
     // cheap early cull before touching the other attribute arrays
@@ -264,8 +293,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
             for (int k = 0; k < 6; ++k) cov3D[k] = cov3D_precomp[6 * (size_t)idx + k];
         } else {
             const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
-            cov3d_from_scale_rot(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2], scale_modifier, q.x, q.y,
-                                 q.z, q.w, cov3D);
+            const float* sc = stage_scales ? s_scales + 3 * threadIdx.x : scales + 3 * (size_t)idx;
+            cov3d_from_scale_rot(sc[0], sc[1], sc[2], scale_modifier, q.x, q.y, q.z, q.w, cov3D);
 #pragma unroll
             for (int k = 0; k < 6; ++k) cov3D_out[6 * (size_t)idx + k] = cov3D[k];
         }
@@ -284,7 +313,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     if (colors_precomp != nullptr) {
         rgb[0] = colors_precomp[3 * idx]; rgb[1] = colors_precomp[3 * idx + 1]; rgb[2] = colors_precomp[3 * idx + 2];
     } else {
-        cmask = sh_to_rgb(D, shs + (size_t)idx * M * 3, x, y, z, s_cam + 32, rgb);
+        cmask = sh_to_rgb(D, stage_sh ? s_sh + 12 * threadIdx.x : shs + (size_t)idx * M * 3, x, y, z, s_cam + 32, rgb);
         clamped[idx] = (uint8_t)cmask;
     }
     const float opacity = opacities[idx];

@@ -111,3 +111,24 @@ def test_non_default_stream_and_noncontiguous_inputs(cuda_device):
         other = GaussianRasterizer(sc.settings())(means2D=None, **kw)
     s.synchronize()
     assert torch.equal(base[0], other[0]) and torch.equal(base[1], other[1])
+
+
+def test_misaligned_views_take_the_plain_load_path(cuda_device):
+    """preprocess stages 16-byte-aligned attribute slices with TMA bulk copies; a contiguous view that starts
+    4 bytes into its storage must give the same answer through the fallback loads."""
+    sc = _scene(cuda_device, P=1500, W=96, H=64)
+    base = GaussianRasterizer(sc.settings())(means2D=None, **sc.raster_kwargs())
+    kw = sc.raster_kwargs()
+
+    def shifted(t):
+        buf = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+        buf[1:] = t.reshape(-1)
+        v = buf[1:].view(t.shape)
+        assert v.data_ptr() % 16 != 0 and v.is_contiguous()
+        return v
+
+    for k in ("means3D", "scales", "shs"):
+        kw[k] = shifted(kw[k])
+    other = GaussianRasterizer(sc.settings())(means2D=None, **kw)
+    for a, b in zip(base, other):
+        assert torch.equal(a, b)
