@@ -301,41 +301,58 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
         project_gaussian(x, y, z, v, m, cov3D, W, H, tan_fovx, tan_fovy, focal_x, focal_y, grid_x, grid_y, o);
         vis = o.visible;
     }
+    Rec r;
     if (!vis) {
         radii[idx] = 0;
         tiles_touched[idx] = 0;
         depth_key[idx] = 0xFFFFFFFFu;
         rect[idx] = make_uint2(0u, 0u);
-        return;
-    }
-    float rgb[3];
-    uint32_t cmask = 0;
-    if (colors_precomp != nullptr) {
-        rgb[0] = colors_precomp[3 * idx]; rgb[1] = colors_precomp[3 * idx + 1]; rgb[2] = colors_precomp[3 * idx + 2];
+        r.a = r.b = r.c = make_float4(0.f, 0.f, 0.f, 0.f);  // never read: culled Gaussians emit no instance
     } else {
-        cmask = sh_to_rgb(D, stage_sh ? s_sh + 12 * threadIdx.x : shs + (size_t)idx * M * 3, x, y, z, s_cam + 32, rgb);
-        clamped[idx] = (uint8_t)cmask;
+        float rgb[3];
+        uint32_t cmask = 0;
+        if (colors_precomp != nullptr) {
+            rgb[0] = colors_precomp[3 * idx]; rgb[1] = colors_precomp[3 * idx + 1]; rgb[2] = colors_precomp[3 * idx + 2];
+        } else {
+            cmask = sh_to_rgb(D, stage_sh ? s_sh + 12 * threadIdx.x : shs + (size_t)idx * M * 3, x, y, z, s_cam + 32, rgb);
+            clamped[idx] = (uint8_t)cmask;
+        }
+        const float opacity = opacities[idx];
+        float hx, hy, thr;
+        alpha_footprint(o.conx, o.cony, o.conz, opacity, o.radius, hx, hy, thr);
+        r.a = make_float4(o.px, o.py, pack_extents(hx, hy), thr);
+        r.b = make_float4(o.conx, o.cony, o.conz, opacity);
+        r.c = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
+        radii[idx] = o.radius;
+        uint32_t ly0 = o.ymin, ly1 = o.ymax;
+        if (row_stride > 1) {
+            // rows of [ymin, ymax) owned by this band (r % stride == phase), expressed as local row indices
+            const uint32_t st = (uint32_t)row_stride, ph = (uint32_t)row_phase;
+            const uint32_t first = o.ymin + ((ph + st - o.ymin % st) % st);
+            if (first < o.ymax) { ly0 = (first - ph) / st; ly1 = ly0 + (o.ymax - 1 - first) / st + 1; }
+            else { ly0 = 0; ly1 = 0; }
+        }
+        tiles_touched[idx] = (o.xmax - o.xmin) * (ly1 - ly0);
+        depth_key[idx] = __float_as_uint(o.depth);
+        rect[idx] = make_uint2(o.xmin | (o.xmax << 16), ly0 | (ly1 << 16));
     }
-    const float opacity = opacities[idx];
-    float hx, hy, thr;
-    alpha_footprint(o.conx, o.cony, o.conz, opacity, o.radius, hx, hy, thr);
-    Rec r;
-    r.a = make_float4(o.px, o.py, pack_extents(hx, hy), thr);
-    r.b = make_float4(o.conx, o.cony, o.conz, opacity);
-    r.c = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
-    rec[idx] = r;
-    radii[idx] = o.radius;
-    uint32_t ly0 = o.ymin, ly1 = o.ymax;
-    if (row_stride > 1) {
-        // rows of [ymin, ymax) owned by this band (r % stride == phase), expressed as local row indices
-        const uint32_t st = (uint32_t)row_stride, ph = (uint32_t)row_phase;
-        const uint32_t first = o.ymin + ((ph + st - o.ymin % st) % st);
-        if (first < o.ymax) { ly0 = (first - ph) / st; ly1 = ly0 + (o.ymax - 1 - first) / st + 1; }
-        else { ly0 = 0; ly1 = 0; }
+    // The 256 records of a full CTA are one contiguous 12 KB range: each thread drops its record into its own
+    // (already consumed) 48-byte SH slot and one thread writes the range back with a TMA bulk store.
+    if (full_cta) {
+        float4* slot = reinterpret_cast<float4*>(s_sh) + 3 * threadIdx.x;
+        slot[0] = r.a; slot[1] = r.b; slot[2] = r.c;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rec + cta_first),
+                         "r"(smem_u32(s_sh)), "r"(256u * 48u)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else if (vis) {
+        rec[idx] = r;
     }
-    tiles_touched[idx] = (o.xmax - o.xmin) * (ly1 - ly0);
-    depth_key[idx] = __float_as_uint(o.depth);
-    rect[idx] = make_uint2(o.xmin | (o.xmax << 16), ly0 | (ly1 << 16));
 }
 
 // checkFrustum, rasterizer_impl.cu:54-66

@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
     // decoupled look-back over preceding tiles for digit `tid`
     uint32_t excl = 0;
     if (precomputed_offsets) {
-        excl = *my_lb;  // exclusive count of this digit in all earlier tiles (radix_tile_scan_kernel)
+        // exclusive count of this digit in all earlier tiles (radix_tile_scan_kernel, digit-major layout)
+        excl = lookback[(size_t)tid * gridDim.x + tile];
     } else if (tile > 0) {
         // windowed look-back: fetch up to 4 predecessor states per round trip instead of one
         int t = (int)tile - 1;
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
 // time (4 B per pair) to precompute the offsets is cheaper.
 __global__ void __launch_bounds__(SORT_THREADS) radix_tile_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
                                                                       int shift, int bits,
-                                                                      uint32_t* __restrict__ tile_hist /*[tiles][256]*/) {
+                                                                      uint32_t* __restrict__ tile_hist /*[256][tiles]*/) {
     __shared__ uint32_t s_hist[256];
     const int tid = threadIdx.x;
     s_hist[tid] = 0;
@@ -258,24 +259,28 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_tile_hist_kernel(const uin
         }
     }
     __syncthreads();
-    tile_hist[(size_t)blockIdx.x * 256 + tid] = s_hist[tid];
+    tile_hist[(size_t)tid * gridDim.x + blockIdx.x] = s_hist[tid];  // digit-major: the scan reads contiguously
 }
 
-// one CTA per digit: exclusive scan of that digit's counts over the tiles (in place) + the digit total
-__global__ void __launch_bounds__(256) radix_tile_scan_kernel(uint32_t* __restrict__ tile_hist, uint32_t tiles,
-                                                              uint32_t* __restrict__ digit_totals /*[256]*/) {
+// one CTA per digit: exclusive scan of that digit's contiguous row of tile counts (in place) + the digit total
+__global__ void __launch_bounds__(256) radix_tile_scan_kernel(uint32_t* __restrict__ tile_hist /*[256][tiles]*/,
+                                                              uint32_t tiles, uint32_t* __restrict__ digit_totals) {
     __shared__ uint32_t s_scan[8];
-    const uint32_t d = blockIdx.x;
+    uint32_t* row = tile_hist + (size_t)blockIdx.x * tiles;
     uint32_t running = 0;
-    for (uint32_t t0 = 0; t0 < tiles; t0 += 256) {
-        const uint32_t t = t0 + threadIdx.x;
-        const uint32_t v = t < tiles ? tile_hist[(size_t)t * 256 + d] : 0u;
+    constexpr uint32_t PER = 16;  // values per thread per chunk
+    for (uint32_t t0 = 0; t0 < tiles; t0 += 256 * PER) {
+        const uint32_t base = t0 + threadIdx.x * PER;
+        uint32_t v[PER], sum = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < PER; ++i) { v[i] = base + i < tiles ? row[base + i] : 0u; sum += v[i]; }
         uint32_t chunk_total;
-        const uint32_t ex = block_exclusive_scan_256(v, s_scan, &chunk_total);
-        if (t < tiles) tile_hist[(size_t)t * 256 + d] = running + ex;
+        uint32_t ex = running + block_exclusive_scan_256(sum, s_scan, &chunk_total);
+#pragma unroll
+        for (uint32_t i = 0; i < PER; ++i) { if (base + i < tiles) row[base + i] = ex; ex += v[i]; }
         running += chunk_total;
     }
-    if (threadIdx.x == 0) digit_totals[d] = running;
+    if (threadIdx.x == 0) digit_totals[blockIdx.x] = running;
 }
 
 // Sorts n pairs on bits [0, total_bits).  Input in (keys_a, vals_a); (keys_b, vals_b) is the
