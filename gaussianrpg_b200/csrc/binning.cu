@@ -113,14 +113,22 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __r
                                                              const uint32_t* __restrict__ chunk_start, uint32_t P,
                                                              uint32_t R, uint32_t grid_x,
                                                              uint32_t* __restrict__ inst_tile,
-                                                             uint32_t* __restrict__ inst_gauss) {
+                                                             uint32_t* __restrict__ inst_gauss,
+                                                             uint32_t* __restrict__ tile_hist /*[256][sort tiles]*/,
+                                                             uint32_t sort_tiles, uint32_t digit_mask) {
+    // A CTA writes 8 x 1024 consecutive instances = exactly two 4096-key tiles of the tile-id sort, so the
+    // digit histograms of that sort's first pass are accumulated here instead of re-reading the keys.
+    __shared__ uint32_t s_hist[2][256];
+    s_hist[0][threadIdx.x] = 0;
+    s_hist[1][threadIdx.x] = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
+    const int half = (threadIdx.x >> 5) >> 2;  // warps 0-3 -> first sort tile, 4-7 -> second
     const uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long lo64 = (unsigned long long)chunk * EMIT_CHUNK;
-    if (lo64 >= R) return;
-    uint32_t cur = (uint32_t)lo64;
-    const uint32_t hi = min(R, cur + EMIT_CHUNK);
-    uint32_t pos = chunk_start[chunk];
+    uint32_t cur = lo64 < R ? (uint32_t)lo64 : R;
+    const uint32_t hi = lo64 < R ? min(R, cur + EMIT_CHUNK) : R;
+    uint32_t pos = lo64 < R ? chunk_start[chunk] : P;
     while (cur < hi && pos < P) {
         const uint32_t p = pos + lane;
         uint32_t g = 0, off = 0xFFFFFFFFu, x0 = 0, y0 = 0, w = 1, end = 0;
@@ -151,13 +159,19 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __r
             if (k < stop) {
                 const uint32_t m = k - o_off;
                 const uint32_t ty = m / o_w, tx = m - ty * o_w;
-                inst_tile[k] = (o_y0 + ty) * grid_x + (o_x0 + tx);
+                const uint32_t tile_id = (o_y0 + ty) * grid_x + (o_x0 + tx);
+                inst_tile[k] = tile_id;
                 inst_gauss[k] = o_g;
+                atomicAdd(&s_hist[half][tile_id & digit_mask], 1u);
             }
         }
         if (stop > cur) cur = stop;
         pos += 32;
     }
+    __syncthreads();
+    const uint32_t t0 = blockIdx.x * 2;
+    if (t0 < sort_tiles) tile_hist[(size_t)threadIdx.x * sort_tiles + t0] = s_hist[0][threadIdx.x];
+    if (t0 + 1 < sort_tiles) tile_hist[(size_t)threadIdx.x * sort_tiles + t0 + 1] = s_hist[1][threadIdx.x];
 }
 
 // ---- 5. tile ranges (identifyTileRanges, rasterizer_impl.cu:116-138) -----------------------
@@ -274,10 +288,15 @@ void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tile
         gs += align_up((((size_t)P + SCAN_TILE - 1) / SCAN_TILE + 2) * 8, 256) + 256;
         const uint32_t* chunk_start = (const uint32_t*)gs;
         const unsigned warps = (unsigned)((R + EMIT_CHUNK - 1) / EMIT_CHUNK);
-        emit_instances_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(sorted_idx, offsets, rect, chunk_start, (uint32_t)P,
-                                                                   (uint32_t)R, grid_x, k0, v0);
+        static_assert(EMIT_CHUNK * 8 == 2 * SORT_TILE, "an emit CTA must cover exactly two sort tiles");
+        const uint32_t sort_tiles = (uint32_t)sort_num_tiles(R);
+        emit_instances_kernel<<<(sort_tiles + 1) / 2, 256, 0, stream>>>(
+            sorted_idx, offsets, rect, chunk_start, (uint32_t)P, (uint32_t)R, grid_x, k0, v0, sort_first_pass_hist(aux),
+            sort_tiles, (1u << plan.bits[0]) - 1u);
+        (void)warps;
     }
-    onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream, "tile_sort_hist", "tile_sort_pass");
+    onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream, "tile_sort_hist", "tile_sort_pass",
+                        /*iota_values=*/false, /*first_hist_ready=*/true);
     ProfScope ps("tile_ranges", stream);
     tile_ranges_kernel<<<(unsigned)((R + 1023) / 1024), 256, 0, stream>>>(tile_keys, (uint32_t)R, ranges);
 }

@@ -151,9 +151,11 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
         uint32_t peers = 0xffffffffu;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? bal : ~bal;
+            if (b < bits) {  // warp-uniform: digits narrower than 8 bits need fewer ballots
+                const bool bit = (d >> b) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+            }
         }
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
@@ -283,6 +285,8 @@ __global__ void __launch_bounds__(256) radix_tile_scan_kernel(uint32_t* __restri
     if (threadIdx.x == 0) digit_totals[blockIdx.x] = running;
 }
 
+static inline uint32_t* sort_first_pass_hist(uint32_t* aux) { return aux + SORT_MAX_PASSES * (256 + 64); }
+
 // Sorts n pairs on bits [0, total_bits).  Input in (keys_a, vals_a); (keys_b, vals_b) is the
 // ping-pong partner.  Returns true when the sorted result ends in the *_a buffers, false for *_b.
 // `aux` must hold SORT_MAX_PASSES*(256+64) uint32 + SORT_MAX_PASSES*tiles*256 uint32 and is
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(256) radix_tile_scan_kernel(uint32_t* __restri
 static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                                        long long n, int total_bits, uint32_t* aux, int num_sms, cudaStream_t stream,
                                        const char* hist_name = "sort_hist", const char* pass_name = "sort_pass",
-                                       bool iota_values = false) {
+                                       bool iota_values = false, bool first_hist_ready = false) {
     if (n <= 0) return true;
     SortPlan plan = make_sort_plan(total_bits);
     size_t tiles = sort_num_tiles(n);
@@ -307,8 +311,9 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
         uint32_t* tile_offsets = lookback + (size_t)p * tiles * 256;
         {
             ProfScope ps(hist_name, stream);
-            radix_tile_hist_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(ki, (uint32_t)n, plan.shift[p],
-                                                                                plan.bits[p], tile_offsets);
+            if (!(first_hist_ready && p == 0))  // the producer of the keys already filled pass 0's tile histograms
+                radix_tile_hist_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(ki, (uint32_t)n, plan.shift[p],
+                                                                                    plan.bits[p], tile_offsets);
             radix_tile_scan_kernel<<<256, 256, 0, stream>>>(tile_offsets, (uint32_t)tiles, hist + p * 256);
         }
         ProfScope ps(pass_name, stream);
