@@ -63,9 +63,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dalphas,
     const float* __restrict__ dL_dpixel_semantics, float* __restrict__ grad_rec /*[P][12]*/,
     float* __restrict__ dL_dsemantics /*[P][S]*/, int HL, int row_stride, int row_phase) {
-    __shared__ float4 s_a[BWD_BATCH];
-    __shared__ float4 s_b[BWD_BATCH];
-    __shared__ float4 s_c[BWD_BATCH];
+    __shared__ __align__(16) float4 s_rec[BWD_BATCH * 3];  // staged records, 48-byte stride
     __shared__ uint32_t s_id[BWD_BATCH];
     __shared__ int s_maxlast[8];
     __shared__ uint8_t s_q[8][BWD_BATCH];
@@ -126,9 +124,9 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
             // slot t holds 0-based position top-1-t: ascending slot = back-to-front
             const uint32_t id = point_list[range.x + top - 1 - tid];
             const float4* r = reinterpret_cast<const float4*>(rec + id);
-            s_a[tid] = __ldg(r);
-            s_b[tid] = __ldg(r + 1);
-            s_c[tid] = __ldg(r + 2);
+            s_rec[3 * tid] = __ldg(r);
+            s_rec[3 * tid + 1] = __ldg(r + 1);
+            s_rec[3 * tid + 2] = __ldg(r + 2);
             s_id[tid] = id;
         }
         __syncthreads();
@@ -140,7 +138,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
         for (int g0 = 0; g0 < cnt; g0 += 32) {
             const int j = g0 + lane;
             // slots whose position lies behind every pixel's last contributor cannot receive gradient
-            const bool hit = j < cnt && (top - 1 - j) < wmax && footprint_hits_exact(s_a[j], s_b[j], bx_lo, bx_hi, by_lo, by_hi);
+            const bool hit = j < cnt && (top - 1 - j) < wmax && footprint_hits_exact(s_rec[3 * j], s_rec[3 * j + 1], bx_lo, bx_hi, by_lo, by_hi);
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
             if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
             n_q += __popc(m);
@@ -151,8 +149,8 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
             for (int qi = 0; qi < n_q; ++qi) {
                 const int k = q[qi];
                 const int pos = top - 1 - k;  // 0-based position in the tile's range
-                const float4 a = s_a[k];
-                const float4 b = s_b[k];
+                const float4 a = s_rec[3 * k];
+                const float4 b = s_rec[3 * k + 1];
                 const uint32_t gid = s_id[k];
                 const float dx = a.x - pxf, dy = a.y - pyf;
                 const float power = ffma(ffma(dx, fmul(dx, b.x), fmul(dy, fmul(dy, b.z))), -0.5f, -fmul(dy, fmul(dx, b.y)));
@@ -169,7 +167,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
 #pragma unroll
                 for (int i = 0; i < (SB > 0 ? SB : 1); ++i) g_sem[i] = 0.f;
                 // all loads happen before the divergent section
-                const float4 c = s_c[k];
+                const float4 c = s_rec[3 * k + 2];
                 float sv[SB > 0 ? SB : 1];
                 if (SB > 0) {
                     const float* sp = semantics + (size_t)gid * S;
