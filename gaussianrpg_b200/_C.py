@@ -55,7 +55,7 @@ def _layouts(P: int, R: int, W: int, H: int):
 
 def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
-                        degree, campos, prefiltered, debug, *, _band=(1, 0)
+                        degree, campos, prefiltered, debug, *, _band=(1, 0), _forward_only=False
                         ) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
                                    torch.Tensor, torch.Tensor, torch.Tensor]:
     """RasterizeGaussiansCUDA (rasterize_points.cu:35-124).
@@ -129,6 +129,7 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
     a.geom_ws, a.image_ws, a.binning_ws = geom.data_ptr(), img.data_ptr(), None
     a.stream = _stream()
     a.tile_row_stride, a.tile_row_phase = stride, phase
+    a.forward_only = int(bool(_forward_only))
 
     with torch.cuda.device(dev):
         n = C.c_int(0)

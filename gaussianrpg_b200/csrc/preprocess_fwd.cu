@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
     const float* __restrict__ viewmatrix, const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
     int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
-    int prefiltered, int row_stride, int row_phase, int* __restrict__ radii, Rec* __restrict__ rec, uint32_t* __restrict__ depth_key,
+    int prefiltered, int row_stride, int row_phase, int forward_only, int* __restrict__ radii, Rec* __restrict__ rec, uint32_t* __restrict__ depth_key,
     uint2* __restrict__ rect, uint32_t* __restrict__ tiles_touched, float* __restrict__ cov3D_out,
     uint8_t* __restrict__ clamped) {
     __shared__ float s_cam[35];
@@ -295,8 +295,10 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
             const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
             const float* sc = stage_scales ? s_scales + 3 * threadIdx.x : scales + 3 * (size_t)idx;
             cov3d_from_scale_rot(sc[0], sc[1], sc[2], scale_modifier, q.x, q.y, q.z, q.w, cov3D);
+            if (!forward_only) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) cov3D_out[6 * (size_t)idx + k] = cov3D[k];
+                for (int k = 0; k < 6; ++k) cov3D_out[6 * (size_t)idx + k] = cov3D[k];
+            }
         }
         project_gaussian(x, y, z, v, m, cov3D, W, H, tan_fovx, tan_fovy, focal_x, focal_y, grid_x, grid_y, o);
         vis = o.visible;
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
             rgb[0] = colors_precomp[3 * idx]; rgb[1] = colors_precomp[3 * idx + 1]; rgb[2] = colors_precomp[3 * idx + 2];
         } else {
             cmask = sh_to_rgb(D, stage_sh ? s_sh + 12 * threadIdx.x : shs + (size_t)idx * M * 3, x, y, z, s_cam + 32, rgb);
-            clamped[idx] = (uint8_t)cmask;
+            if (!forward_only) clamped[idx] = (uint8_t)cmask;
         }
         const float opacity = opacities[idx];
         float hx, hy, thr;
@@ -404,7 +406,7 @@ void launch_preprocess_fwd(const grpg_forward_args* a, float focal_x, float foca
     preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs, a->cov3D_precomp,
         a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos, a->width, a->height, a->tan_fovx, a->tan_fovy,
-        focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->tile_row_stride, a->tile_row_phase, a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped);
+        focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->tile_row_stride, a->tile_row_phase, a->forward_only, a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped);
 }
 
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream) {

@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 // ---- one onesweep digit pass -----------------------------------------------------------
-__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_pass_kernel(
+__global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift, int bits,
     const uint32_t* __restrict__ hist /*[256] for this pass*/, uint32_t* __restrict__ tile_counter,

@@ -57,8 +57,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         native_args = (rs.bg, means3D, colors_precomp, semantics, opacities, scales, rotations, rs.scale_modifier,
                        cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
                        rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        # when no input requires grad (eval / torch.no_grad) the backward-only state is not materialised
+        fwd_only = not any(ctx.needs_input_grad)
         (num_rendered, color, depth, alpha, semantic, radii, geom, binning, img) = _call_with_snapshot(
-            _C.rasterize_gaussians, native_args, rs.debug, "snapshot_fw.dump", "forward")
+            lambda *a_: _C.rasterize_gaussians(*a_, _forward_only=fwd_only), native_args, rs.debug, "snapshot_fw.dump",
+            "forward")
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.tensor_inputs = [isinstance(t, torch.Tensor) for t in (means3D, means2D, sh, colors_precomp, semantics,

@@ -115,6 +115,9 @@ typedef struct grpg_forward_args {
      * [C, rows_local*16, W] (band row i = tile row i*k + phase).  radii stay global.  stride <= 1 = whole frame. */
     int tile_row_stride;
     int tile_row_phase;
+    /* non-zero: no backward will follow (inference): the per-Gaussian cov3D / SH-clamp state that only
+     * grpg_backward reads is not written (saves 25 B per visible Gaussian of HBM writes) */
+    int forward_only;
 } grpg_forward_args;
 
 /* number of tile rows owned by (stride, phase) for an image of `height` pixels, and the pixel height of

@@ -6,4 +6,4 @@ import json
 d=json.load(open('gpurun_out/bench_ours.json'))
 print('fwd_ms',d['fwd_ms'],'step_ms',d['ms_per_step'],'e2e',d['e2e']['value'],'check',d.get('index_check'))
 print({k:round(v['ms_per_step'],4) for k,v in d['kernels'].items()})"
-echo "== ncu blend"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:"blend_fwd|blend_bwd|emit|onesweep" -s 11 -c 11 -f -o gpurun_out/prof_r1c python tools/one_step.py 2 > gpurun_out/ncu_full_c.log 2>&1; tail -2 gpurun_out/ncu_full_c.log
+
