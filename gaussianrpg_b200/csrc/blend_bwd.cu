@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     __shared__ __align__(16) float4 s_rec[BWD_BATCH * 3];  // staged records, 48-byte stride
     __shared__ uint32_t s_id[BWD_BATCH];
     __shared__ int s_maxlast[8];
-    __shared__ uint8_t s_q[8][BWD_BATCH];
+    __shared__ uint16_t s_q[8][BWD_BATCH];  // per-warp queue of surviving slots, as byte offsets (slot * 48)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
@@ -133,24 +133,27 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
         if (wmax <= top - cnt) continue;  // every pixel of this warp ended before this batch
 
         // phase 1: footprint test of the whole batch, survivors compacted into a per-warp byte queue
-        uint8_t* q = s_q[warp];
+        uint16_t* q = s_q[warp];
+        const char* rec_base = reinterpret_cast<const char*>(s_rec);
         int n_q = 0;
         for (int g0 = 0; g0 < cnt; g0 += 32) {
             const int j = g0 + lane;
             // slots whose position lies behind every pixel's last contributor cannot receive gradient
             const bool hit = j < cnt && (top - 1 - j) < wmax && footprint_hits_exact(s_rec[3 * j], s_rec[3 * j + 1], bx_lo, bx_hi, by_lo, by_hi);
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
+            if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(j * 48);
             n_q += __popc(m);
         }
         __syncwarp();
         // phase 2: back-to-front replay of the survivors
         {
             for (int qi = 0; qi < n_q; ++qi) {
-                const int k = q[qi];
+                const uint32_t off = q[qi];
+                const int k = (int)(off / 48u);
+                const float4* rk = reinterpret_cast<const float4*>(rec_base + off);
                 const int pos = top - 1 - k;  // 0-based position in the tile's range
-                const float4 a = s_rec[3 * k];
-                const float4 b = s_rec[3 * k + 1];
+                const float4 a = rk[0];
+                const float4 b = rk[1];
                 const uint32_t gid = s_id[k];
                 const float dx = a.x - pxf, dy = a.y - pyf;
                 const float power = ffma(ffma(dx, fmul(dx, b.x), fmul(dy, fmul(dy, b.z))), -0.5f, -fmul(dy, fmul(dx, b.y)));
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
 #pragma unroll
                 for (int i = 0; i < (SB > 0 ? SB : 1); ++i) g_sem[i] = 0.f;
                 // all loads happen before the divergent section
-                const float4 c = s_rec[3 * k + 2];
+                const float4 c = rk[2];
                 float sv[SB > 0 ? SB : 1];
                 if (SB > 0) {
                     const float* sp = semantics + (size_t)gid * S;
