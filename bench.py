@@ -174,7 +174,8 @@ def cpu_baseline_sample(sc_cpu, n_tiles=24):
     lens = binned["ranges"][:, 1].astype(np.int64) - binned["ranges"][:, 0]
     rng = np.random.default_rng(0)
     picks = rng.permutation(gx * gy)[:n_tiles]  # uniform random tiles; cost is extrapolated per instance
-    torch.set_num_threads(os.cpu_count() or 1)
+    # 16x16-pixel tensors: more than a few threads only adds fork/join overhead; the count used is reported
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
     secs, n_inst, n_done = torch_blend.time_tiles(pre, binned, sc_cpu, [int(t) for t in picks], budget_s=20.0)
     est_total = secs / max(1, n_inst) * float(lens.sum()) + t_pre
     return {"value": 1.0 / est_total, "unit": "iters/s", "cores": torch.get_num_threads(), "kind": "port",
