@@ -209,9 +209,15 @@ def main():
 
     if args.impl == "ours" and dist_on:
         from gaussianrpg_b200 import dist as gdist
+        clocks = ClockSampler(local_rank) if rank == 0 else None
         result = gdist.bench_sharded(args, sc_cpu, dev, rank, world)
         if rank == 0:
+            clk = clocks.stop()
+            result["clocks"] = {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]}
             print(json.dumps(result))
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
     H, W = sc_cpu.height, sc_cpu.width
