@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
 #pragma unroll
     for (int i = 0; i < SCAN_IPT; ++i) {
         uint32_t j = base + i;
-        v[i] = j < P ? tiles_touched[sorted_idx[j]] : 0u;
+        // the last depth-sort pass left tiles_touched[sorted_idx[j]] in offsets[j]; it is overwritten below with
+        // the exclusive prefix (each CTA reads its own range before writing it)
+        v[i] = j < P ? offsets[j] : 0u;
         sum += v[i];
     }
     uint32_t block_total;
@@ -249,7 +251,8 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
 
     // values start as the identity permutation: generated inside the first digit pass, no iota kernel
     bool in_a = onesweep_sort_pairs(depth_key, sorted_idx, keys_b, vals_b, P, 32, aux, num_sms, stream,
-                                    "depth_sort_hist", "depth_sort_pass", /*iota_values=*/true);
+                                    "depth_sort_hist", "depth_sort_pass", /*iota_values=*/true,
+                                    /*first_hist_ready=*/false, /*gather_src=*/tiles_touched, /*gather_dst=*/offsets);
     if (!in_a) {  // 32 bits -> 4 passes -> always lands back in the a-buffers; kept for safety
         cudaMemcpyAsync(depth_key, keys_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(sorted_idx, vals_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);

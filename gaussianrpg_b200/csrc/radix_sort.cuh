@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift, int bits,
     const uint32_t* __restrict__ hist /*[256] for this pass*/, uint32_t* __restrict__ tile_counter,
-    uint32_t* __restrict__ lookback /*[tiles][256]*/, int iota_values, int precomputed_offsets) {
+    uint32_t* __restrict__ lookback /*[tiles][256]*/, int iota_values, int precomputed_offsets,
+    const uint32_t* __restrict__ gather_src, uint32_t* __restrict__ gather_dst) {
     __shared__ uint32_t s_warp_hist[8][256];
     __shared__ uint32_t s_local_start[256];
     __shared__ uint32_t s_bin_base[256];
@@ -226,7 +227,10 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
             uint32_t kk = s_keys[p];
             uint32_t o = s_bin_base[(kk >> shift) & mask] + p;
             keys_out[o] = kk;
-            vals_out[o] = s_vals[p];
+            const uint32_t vv = s_vals[p];
+            vals_out[o] = vv;
+            // optional payload gathered through the sorted value (the scan of tile counts then reads it in order)
+            if (gather_src != nullptr) gather_dst[o] = gather_src[vv];
         }
     }
 }
@@ -283,132 +287,6 @@ __global__ void __launch_bounds__(256) radix_tile_scan_kernel(uint32_t* __restri
     if (threadIdx.x == 0) digit_totals[blockIdx.x] = running;
 }
 
-// ---- scatter pass with counting ranks (digits of at most 7 bits) ---------------------------------------------------
-// The ballot ranking above costs ~4 warp instructions per key (8 ballots + bookkeeping, 64 % issue utilisation at
-// 2.9 TB/s).  For narrow digits the classic counting rank is cheaper: every thread owns 16 CONSECUTIVE keys, bumps
-// a private 16-bit counter per digit, one exclusive scan over the counters in (digit-major, thread) order turns them
-// into tile-local rank bases, and each key's rank is base + its arrival number inside the thread.  Stable by
-// construction.  Counters: 128 digits x 256 threads x 2 B = 64 KB (padded against bank conflicts), reused afterwards
-// as the staging buffer for the coalesced write-out.
-constexpr int CS_DIG = 128;
-constexpr int CS_CNT_WORDS = CS_DIG * SORT_THREADS / 2;           // 16384 words of 2 x u16
-constexpr int CS_PAD_WORDS = (CS_CNT_WORDS / 64) * 4;             // 4 pad words per 64: rows stay 16-byte aligned
-constexpr size_t CS_SMEM_BYTES = (size_t)(CS_CNT_WORDS + CS_PAD_WORDS) * 4 + (CS_DIG + 16) * 4;
-
-__device__ __forceinline__ uint32_t cs_entry(uint32_t d, uint32_t t) {  // u16 index of counter (digit d, thread t)
-    const uint32_t e = d * SORT_THREADS + t;
-    return e + ((e >> 7) << 3);  // every 128 entries (64 words) are followed by 8 pad entries (4 words)
-}
-
-__global__ void __launch_bounds__(SORT_THREADS, 3) radix_scatter_count_kernel(
-    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, uint32_t n, int shift, int bits, const uint32_t* __restrict__ digit_totals /*[256]*/,
-    const uint32_t* __restrict__ tile_offsets /*[256][tiles]*/) {
-    extern __shared__ __align__(16) unsigned char cs_smem[];
-    uint16_t* cnt = reinterpret_cast<uint16_t*>(cs_smem);
-    uint32_t* cntw = reinterpret_cast<uint32_t*>(cs_smem);
-    uint32_t* s_base = cntw + CS_CNT_WORDS + CS_PAD_WORDS;  // [128]
-    uint32_t* s_scan = s_base + CS_DIG;                     // [8]
-    const uint32_t t = threadIdx.x, tile = blockIdx.x, tile_base = tile * SORT_TILE;
-    const uint32_t mask = (1u << bits) - 1u;
-
-    // zero the counters (16-byte stores)
-    {
-        uint4* z = reinterpret_cast<uint4*>(cs_smem);
-        constexpr int N16 = (CS_CNT_WORDS + CS_PAD_WORDS) / 4;
-        for (int i = t; i < N16; i += SORT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    // blocked loads: thread t owns the 16 consecutive pairs starting at tile_base + 16 t
-    uint32_t key[SORT_IPT], val[SORT_IPT];
-    const uint32_t base = tile_base + t * SORT_IPT;
-    if (base + SORT_IPT <= n) {
-#pragma unroll
-        for (int q = 0; q < SORT_IPT / 4; ++q) {
-            const uint4 k4 = *reinterpret_cast<const uint4*>(keys_in + base + 4 * q);
-            const uint4 v4 = *reinterpret_cast<const uint4*>(vals_in + base + 4 * q);
-            key[4 * q] = k4.x; key[4 * q + 1] = k4.y; key[4 * q + 2] = k4.z; key[4 * q + 3] = k4.w;
-            val[4 * q] = v4.x; val[4 * q + 1] = v4.y; val[4 * q + 2] = v4.z; val[4 * q + 3] = v4.w;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < SORT_IPT; ++i) {
-            key[i] = base + i < n ? keys_in[base + i] : 0xFFFFFFFFu;  // pads rank last inside the last digit
-            val[i] = base + i < n ? vals_in[base + i] : 0u;
-        }
-    }
-    __syncthreads();
-
-    // phase 1: private counters; remember each key's arrival number among equal digits of this thread (4 bits)
-    unsigned long long arrival = 0ull;
-#pragma unroll
-    for (int i = 0; i < SORT_IPT; ++i) {
-        const uint32_t d = (key[i] >> shift) & mask;
-        uint16_t* c = cnt + cs_entry(d, t);
-        const uint32_t old = *c;
-        *c = (uint16_t)(old + 1);
-        arrival |= (unsigned long long)old << (4 * i);
-    }
-    __syncthreads();
-
-    // phase 2: exclusive scan of all counters in (digit-major, thread) order; thread t rakes entries [128t, 128t+128)
-    {
-        uint4* row = reinterpret_cast<uint4*>(cntw + t * 68);  // 64 data words + 4 pad words per row
-        uint32_t sum = 0;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const uint4 x = row[q];
-            sum += (x.x & 0xffffu) + (x.x >> 16) + (x.y & 0xffffu) + (x.y >> 16) + (x.z & 0xffffu) + (x.z >> 16) +
-                   (x.w & 0xffffu) + (x.w >> 16);
-        }
-        uint32_t run = block_exclusive_scan_256(sum, s_scan);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            uint4 x = row[q];
-            uint32_t lo, hi;
-            lo = x.x & 0xffffu; hi = x.x >> 16; x.x = run | ((run + lo) << 16); run += lo + hi;
-            lo = x.y & 0xffffu; hi = x.y >> 16; x.y = run | ((run + lo) << 16); run += lo + hi;
-            lo = x.z & 0xffffu; hi = x.z >> 16; x.z = run | ((run + lo) << 16); run += lo + hi;
-            lo = x.w & 0xffffu; hi = x.w >> 16; x.w = run | ((run + lo) << 16); run += lo + hi;
-            row[q] = x;
-        }
-    }
-    __syncthreads();
-
-    // phase 3: ranks, and the per-digit output base (global position of the digit run minus its tile-local start)
-    uint16_t rank[SORT_IPT];
-#pragma unroll
-    for (int i = 0; i < SORT_IPT; ++i) {
-        const uint32_t d = (key[i] >> shift) & mask;
-        rank[i] = (uint16_t)(cnt[cs_entry(d, t)] + (uint32_t)((arrival >> (4 * i)) & 15ull));
-    }
-    const uint32_t gexcl = block_exclusive_scan_256(digit_totals[t], s_scan);
-    if (t < CS_DIG) {
-        const uint32_t local_start = cnt[cs_entry(t, 0)];
-        s_base[t] = gexcl + tile_offsets[(size_t)t * gridDim.x + tile] - local_start;
-    }
-    __syncthreads();  // every rank base has been read: the counter area becomes the staging buffer
-
-    uint32_t* s_keys = cntw;
-    uint32_t* s_vals = cntw + SORT_TILE;
-#pragma unroll
-    for (int i = 0; i < SORT_IPT; ++i) {
-        s_keys[rank[i]] = key[i];
-        s_vals[rank[i]] = val[i];
-    }
-    __syncthreads();
-    const uint32_t valid = (n - tile_base) < (uint32_t)SORT_TILE ? (n - tile_base) : (uint32_t)SORT_TILE;
-#pragma unroll
-    for (int k = 0; k < SORT_IPT; ++k) {
-        const uint32_t p = k * SORT_THREADS + t;
-        if (p < valid) {
-            const uint32_t kk = s_keys[p];
-            const uint32_t o = s_base[(kk >> shift) & mask] + p;
-            keys_out[o] = kk;
-            vals_out[o] = s_vals[p];
-        }
-    }
-}
-
 static inline uint32_t* sort_first_pass_hist(uint32_t* aux) { return aux + SORT_MAX_PASSES * (256 + 64); }
 
 // Sorts n pairs on bits [0, total_bits).  Input in (keys_a, vals_a); (keys_b, vals_b) is the
@@ -418,7 +296,8 @@ static inline uint32_t* sort_first_pass_hist(uint32_t* aux) { return aux + SORT_
 static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                                        long long n, int total_bits, uint32_t* aux, int num_sms, cudaStream_t stream,
                                        const char* hist_name = "sort_hist", const char* pass_name = "sort_pass",
-                                       bool iota_values = false, bool first_hist_ready = false) {
+                                       bool iota_values = false, bool first_hist_ready = false,
+                                       const uint32_t* gather_src = nullptr, uint32_t* gather_dst = nullptr) {
     if (n <= 0) return true;
     SortPlan plan = make_sort_plan(total_bits);
     size_t tiles = sort_num_tiles(n);
@@ -441,20 +320,14 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
             radix_tile_scan_kernel<<<256, 256, 0, stream>>>(tile_offsets, (uint32_t)tiles, hist + p * 256);
         }
         ProfScope ps(pass_name, stream);
-        if (plan.bits[p] <= 7 && !(iota_values && p == 0)) {
-            static bool smem_opt_in = false;
-            if (!smem_opt_in) {
-                cudaFuncSetAttribute(radix_scatter_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)CS_SMEM_BYTES);
-                smem_opt_in = true;
-            }
-            radix_scatter_count_kernel<<<(unsigned)tiles, SORT_THREADS, CS_SMEM_BYTES, stream>>>(
-                ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, tile_offsets);
-        } else {
-            onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
-                ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
-                (iota_values && p == 0) ? 1 : 0, /*precomputed_offsets=*/1);
-        }
+        // (a counting-rank scatter -- private 16-bit counters per thread and digit, one scan over them -- was
+        //  measured for the 7-bit tile passes: 17 % fewer instructions but 104 vs 82 us per pass, bound by the
+        //  dependent shared-memory chains at 3 CTAs/SM; the ballot ranking stays)
+        const bool last = p == plan.passes - 1;
+        onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
+            ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
+            (iota_values && p == 0) ? 1 : 0, /*precomputed_offsets=*/1, last ? gather_src : nullptr,
+            last ? gather_dst : nullptr);
         in_a = !in_a;
     }
     return in_a;
