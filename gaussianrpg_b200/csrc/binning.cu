@@ -251,7 +251,7 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
 
     // values start as the identity permutation: generated inside the first digit pass, no iota kernel
     bool in_a = onesweep_sort_pairs(depth_key, sorted_idx, keys_b, vals_b, P, 32, aux, num_sms, stream,
-                                    "depth_sort_hist", "depth_sort_pass", /*iota_values=*/true,
+                                    "depth_sort_hist", "depth_sort_scan", "depth_sort_pass", /*iota_values=*/true,
                                     /*first_hist_ready=*/false, /*gather_src=*/tiles_touched, /*gather_dst=*/offsets);
     if (!in_a) {  // 32 bits -> 4 passes -> always lands back in the a-buffers; kept for safety
         cudaMemcpyAsync(depth_key, keys_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
@@ -298,7 +298,7 @@ void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tile
             sort_tiles, (1u << plan.bits[0]) - 1u);
         (void)warps;
     }
-    onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream, "tile_sort_hist", "tile_sort_pass",
+    onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream, "tile_sort_hist", "tile_sort_scan", "tile_sort_pass",
                         /*iota_values=*/false, /*first_hist_ready=*/true);
     ProfScope ps("tile_ranges", stream);
     tile_ranges_kernel<<<(unsigned)((R + 1023) / 1024), 256, 0, stream>>>(tile_keys, (uint32_t)R, ranges);

@@ -295,7 +295,8 @@ static inline uint32_t* sort_first_pass_hist(uint32_t* aux) { return aux + SORT_
 // cleared here.
 static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                                        long long n, int total_bits, uint32_t* aux, int num_sms, cudaStream_t stream,
-                                       const char* hist_name = "sort_hist", const char* pass_name = "sort_pass",
+                                       const char* hist_name = "sort_hist", const char* scan_name = "sort_scan",
+                                       const char* pass_name = "sort_pass",
                                        bool iota_values = false, bool first_hist_ready = false,
                                        const uint32_t* gather_src = nullptr, uint32_t* gather_dst = nullptr) {
     if (n <= 0) return true;
@@ -312,11 +313,13 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
         uint32_t* ko = in_a ? keys_b : keys_a;
         uint32_t* vo = in_a ? vals_b : vals_a;
         uint32_t* tile_offsets = lookback + (size_t)p * tiles * 256;
-        {
+        if (!(first_hist_ready && p == 0)) {  // else the producer of the keys already filled pass 0's tile histograms
             ProfScope ps(hist_name, stream);
-            if (!(first_hist_ready && p == 0))  // the producer of the keys already filled pass 0's tile histograms
-                radix_tile_hist_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(ki, (uint32_t)n, plan.shift[p],
-                                                                                    plan.bits[p], tile_offsets);
+            radix_tile_hist_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(ki, (uint32_t)n, plan.shift[p],
+                                                                                plan.bits[p], tile_offsets);
+        }
+        {
+            ProfScope ps(scan_name, stream);
             radix_tile_scan_kernel<<<256, 256, 0, stream>>>(tile_offsets, (uint32_t)tiles, hist + p * 256);
         }
         ProfScope ps(pass_name, stream);

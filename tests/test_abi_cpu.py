@@ -82,3 +82,28 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="no CPU path"):
         GaussianRasterizer(st)(torch.rand(4, 3), None, torch.rand(4, 1), shs=torch.rand(4, 1, 3),
                                scales=torch.rand(4, 3), rotations=torch.rand(4, 4))
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Compile a tiny C program against include/grpg_b200.h and compare sizeof/offsetof of every struct field
+    with the ctypes mirrors in gaussianrpg_b200/_lib.py."""
+    import subprocess
+    structs = {"grpg_forward_args": _lib.ForwardArgs, "grpg_backward_args": _lib.BackwardArgs,
+               "grpg_geom_layout": _lib.GeomLayout, "grpg_binning_layout": _lib.BinningLayout,
+               "grpg_image_layout": _lib.ImageLayout}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grpg_b200.h"', 'int main(void){']
+    for cname, ct in structs.items():
+        lines.append(f'printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append('return 0;}')
+    src = tmp_path / "offsets.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "offsets"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        cname, fname, val = line.split()
+        ct = structs[cname]
+        want = C.sizeof(ct) if fname == "sizeof" else getattr(ct, fname).offset
+        assert int(val) == want, f"{cname}.{fname}: C {val} vs ctypes {want}"
