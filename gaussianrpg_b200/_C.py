@@ -55,7 +55,7 @@ def _layouts(P: int, R: int, W: int, H: int):
 
 def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
-                        degree, campos, prefiltered, debug, *, _band=(1, 0), _forward_only=False
+                        degree, campos, prefiltered, debug, *, _band=(1, 0), _forward_only=False, _peer_frames=None
                         ) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
                                    torch.Tensor, torch.Tensor, torch.Tensor]:
     """RasterizeGaussiansCUDA (rasterize_points.cu:35-124).
@@ -130,6 +130,10 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
     a.stream = _stream()
     a.tile_row_stride, a.tile_row_phase = stride, phase
     a.forward_only = int(bool(_forward_only))
+    if _peer_frames:
+        a.n_peer_frames = len(_peer_frames)
+        for i, ptr in enumerate(_peer_frames):
+            a.peer_frames[i] = int(ptr)
 
     with torch.cuda.device(dev):
         n = C.c_int(0)

@@ -42,6 +42,7 @@ class ForwardArgs(C.Structure):
         ("out_color", _fp), ("out_depth", _fp), ("out_alpha", _fp), ("out_semantic", _fp), ("radii", _fp),
         ("geom_ws", _fp), ("binning_ws", _fp), ("image_ws", _fp), ("stream", _fp),
         ("tile_row_stride", C.c_int), ("tile_row_phase", C.c_int), ("forward_only", C.c_int),
+        ("n_peer_frames", C.c_int), ("peer_frames", _fp * 8),
     ]
 
 

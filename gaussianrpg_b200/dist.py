@@ -108,6 +108,34 @@ def _all_gather_rows(x: torch.Tensor, group, k: int) -> torch.Tensor:
 _EXCHANGE_PLAN = "replicate"  # or "shard"; see _ShardedRasterize.backward
 
 
+class _PeerFrame:
+    """Peer-mapped full-frame output buffer (torch symmetric memory over NVLink).  With it the blend kernel of every
+    rank stores its band's pixels directly into all ranks' frames -- the forward all-gather becomes the kernel's
+    epilogue (peer stores) instead of a separate NCCL collective plus an interleave copy."""
+    _cache = {}
+
+    def __init__(self, channels: int, H: int, W: int, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.frame = symm_mem.empty((channels, H, W), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.frame, group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    @classmethod
+    def get(cls, channels, H, W, device, group):
+        key = (channels, H, W, str(device), id(group))
+        if key not in cls._cache:
+            try:
+                cls._cache[key] = cls(channels, H, W, device, group)
+            except Exception as exc:  # no peer mapping on this system: use the NCCL all-gather
+                cls._cache[key] = None
+                if dist.get_rank(group) == 0:
+                    print(f"[gaussianrpg_b200.dist] symmetric memory unavailable ({exc!r}); using NCCL all-gather")
+        return cls._cache[key]
+
+
+FUSED_FORWARD_GATHER = True  # set False to force the NCCL all-gather path
+
+
 # ---- the sharded operator --------------------------------------------------------------------------
 class _ShardedRasterize(torch.autograd.Function):
     @staticmethod
@@ -117,15 +145,25 @@ class _ShardedRasterize(torch.autograd.Function):
         rs = raster_settings
         k, r = dist.get_world_size(group), dist.get_rank(group)
         H, W = rs.image_height, rs.image_width
+        S_in = int(semantics.shape[1]) if semantics is not None and semantics.ndim == 2 else 0
+        peer = None
+        if FUSED_FORWARD_GATHER and k > 1 and k <= 8 and means3D.is_cuda and dist.get_backend(group) == "nccl":
+            peer = _PeerFrame.get(5 + S_in, H, W, means3D.device, group)
+        if peer is not None:
+            peer.handle.barrier(channel=0)  # every rank has finished reading the previous frame
         out = _C.rasterize_gaussians(rs.bg, means3D, colors_precomp, semantics, opacities, scales, rotations,
                                      rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx,
                                      rs.tanfovy, H, W, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug,
-                                     _band=(k, r))
+                                     _band=(k, r), _peer_frames=peer.ptrs if peer is not None else None)
         R, color_b, depth_b, alpha_b, sem_b, radii, geom, binning, img = out
         S = sem_b.shape[0]
-        packed = pad_band(torch.cat([color_b, depth_b, alpha_b, sem_b], 0), H, k)  # one collective for all planes
-        gathered = _all_gather_rows(packed[None], group, k)
-        frame = bands_to_frame(gathered, H)
+        if peer is not None:
+            peer.handle.barrier(channel=1)  # every rank's band has landed in this rank's frame
+            frame = peer.frame.clone()
+        else:
+            packed = pad_band(torch.cat([color_b, depth_b, alpha_b, sem_b], 0), H, k)  # one collective for all planes
+            gathered = _all_gather_rows(packed[None], group, k)
+            frame = bands_to_frame(gathered, H)
         color, depth, alpha, sem = frame[:3], frame[3:4], frame[4:5], frame[5:5 + S]
         ctx.rs, ctx.group, ctx.R = rs, group, R
         ctx.tensor_inputs = [isinstance(t, torch.Tensor) for t in (means3D, means2D, sh, colors_precomp, semantics,

@@ -118,6 +118,13 @@ typedef struct grpg_forward_args {
     /* non-zero: no backward will follow (inference): the per-Gaussian cov3D / SH-clamp state that only
      * grpg_backward reads is not written (saves 25 B per visible Gaussian of HBM writes) */
     int forward_only;
+    /* Fused band all-gather over NVLink (multi-GPU, with tile_row_stride > 1): when n_peer_frames > 0 the blend
+     * kernel also stores every pixel of its band straight into each peer's FULL frame
+     * peer_frames[i] = float[(5 + S), H, W] (channels: 0-2 colour, 3 depth, 4 alpha, 5.. semantics), addressed
+     * with the true pixel row.  The buffers must be peer-mapped (e.g. torch symmetric memory); the caller
+     * synchronises the ranks around the call. */
+    int n_peer_frames;
+    float* peer_frames[8];
 } grpg_forward_args;
 
 /* number of tile rows owned by (stride, phase) for an image of `height` pixels, and the pixel height of

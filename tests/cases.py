@@ -27,7 +27,33 @@ def golden_cases():
     sc.rotations = None
     sc.name = "precomp"
     cases["precomp"] = sc
+    cases["adversarial"] = adversarial_scene()
     return cases
+
+
+def adversarial_scene(P: int = 3000, W: int = 208, H: int = 160, seed: int = 6):
+    """Inputs chosen to stress the parts of our design that are NOT in the reference: needle-like Gaussians
+    (ill-conditioned conics: the conservative culling must still never drop a contribution), splats hugging the
+    near plane (radii of thousands of pixels), opacities straddling 1/255 and above 1, exact duplicates (depth
+    ties -> stable order), and far-away points."""
+    g = torch.Generator().manual_seed(seed)
+    sc = synthetic.plumbing_scene(P=P, W=W, H=H, S=2, sh_degree=1, seed=seed)
+    n = P // 6
+    # needles: one axis 1000x longer than the others
+    sc.scales[:n] = torch.exp(torch.rand(n, 3, generator=g) * 2 - 7)
+    sc.scales[torch.arange(n), torch.randint(0, 3, (n,), generator=g)] *= 1000.0
+    # near-plane splats
+    sc.means3D[n:2 * n, 2] = 0.2 + torch.rand(n, generator=g) * 0.05
+    sc.scales[n:2 * n] *= 0.2
+    # opacity around the 1/255 threshold, exactly at it, and above one
+    sc.opacities[2 * n:3 * n, 0] = (1.0 / 255.0) * (0.5 + torch.rand(n, generator=g) * 1.5)
+    sc.opacities[3 * n:3 * n + 16, 0] = 1.0 / 255.0
+    sc.opacities[3 * n + 16:3 * n + 64, 0] = 1.0 + torch.rand(48, generator=g)
+    # duplicates (identical depth keys) and far points
+    sc.means3D[4 * n:4 * n + 200] = sc.means3D[4 * n]
+    sc.means3D[5 * n:5 * n + 100, 2] = 500.0 + torch.rand(100, generator=g) * 4000.0
+    sc.name = "adversarial"
+    return sc
 
 
 def loss_grads(sc, seed=7):

@@ -26,14 +26,36 @@ def run(rast_cls, **kw):
     loss.backward()
     return out, {**{k: v.grad for k, v in leaves.items()}, "means2D": m2d.grad}
 
+import gaussianrpg_b200.dist as gdist
+
+def fwd_ms(n=30):
+    rast = ShardedGaussianRasterizer(sc.settings())
+    m2d = torch.zeros(sc.means3D.shape[0], 3, device=dev)
+    with torch.no_grad():
+        for _ in range(5):
+            rast(means3D=sc.means3D, means2D=m2d, opacities=sc.opacities, shs=sc.shs, scales=sc.scales, rotations=sc.rotations)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            rast(means3D=sc.means3D, means2D=m2d, opacities=sc.opacities, shs=sc.shs, scales=sc.scales, rotations=sc.rotations)
+        e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
 ref_out, ref_g = run(GaussianRasterizer)
-sh_out, sh_g = run(ShardedGaussianRasterizer)
-torch.cuda.synchronize()
-ok = all(torch.equal(a, b) for a, b in zip((ref_out[0], ref_out[1], ref_out[2], ref_out[3]), (sh_out[0], sh_out[1], sh_out[2], sh_out[3])))
-errs = {k: cases.rel_err(sh_g[k].cpu().numpy(), ref_g[k].cpu().numpy()) for k in ref_g}
-res = torch.tensor([1.0 if ok else 0.0, max(errs.values())], device=dev)
-dist.all_reduce(res, op=dist.ReduceOp.MIN if False else dist.ReduceOp.MAX)
-if rank == 0:
-    print("images bit-identical on rank0:", ok, "max grad rel err:", errs)
+for fused in (True, False):
+    gdist.FUSED_FORWARD_GATHER = fused
+    for rep in range(3):  # repeated: the peer frame is reused, so a missing barrier would show up as stale rows
+        sh_out, sh_g = run(ShardedGaussianRasterizer)
+    torch.cuda.synchronize()
+    ok = all(torch.equal(a, b) for a, b in zip((ref_out[0], ref_out[1], ref_out[2], ref_out[3]), (sh_out[0], sh_out[1], sh_out[2], sh_out[3])))
+    errs = {k: cases.rel_err(sh_g[k].cpu().numpy(), ref_g[k].cpu().numpy()) for k in ref_g}
+    res = torch.tensor([0.0 if ok else 1.0, max(errs.values())], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    ms = fwd_ms()
+    if rank == 0:
+        print(f"fused_peer_store={fused} peer_frame={'yes' if any(v is not None for v in gdist._PeerFrame._cache.values()) else 'no'}:",
+              "images bit-identical on all ranks:", float(res[0]) == 0.0, "max grad rel err: %.3g" % float(res[1]),
+              "sharded forward %.3f ms" % ms)
 dist.barrier()
 dist.destroy_process_group()
