@@ -151,7 +151,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                  dL_dout_depth, dL_dout_alpha, dL_dout_semantic, sh, degree, campos, geomBuffer, R,
                                  binningBuffer, imageBuffer, alphas, semantics, debug, *, _band=(1, 0), _height=None,
-                                 _width=None, _stage=3, _grad_rec=None, _slice=None):
+                                 _width=None, _stage=3, _grad_rec=None, _slice=None, _peer_grad=None):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:126-220).
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
@@ -160,7 +160,9 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     Keyword-only extras for the multi-GPU path (gaussianrpg_b200.dist): `_band` as in the forward (the pixel
     gradients and `alphas` are then band images and `_height`/`_width` are the frame size); `_stage=1` runs only the
     blend backward and returns (grad_rec[P,12], dL_dsemantic[P,S]); `_stage=2` runs only the per-Gaussian
-    backward for `_slice=(p_begin, p_count)` from `_grad_rec[p_count,12]` and returns p_count-row gradients.
+    backward for `_slice=(p_begin, p_count)` from `_grad_rec[p_count,12]` and returns p_count-row gradients;
+    with `_peer_grad` (peer-mapped pointers to every rank's full [P,12] record buffer) stage 2 sums the records
+    over the ranks while loading them instead of reading `_grad_rec`.
     """
     _require_cuda()
     lib = _lib.load()
@@ -234,6 +236,10 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     a.stream = _stream()
     a.tile_row_stride, a.tile_row_phase = stride, phase
     a.stages, a.p_begin, a.p_count = int(_stage), p_begin, p_count
+    if _peer_grad:
+        a.n_peer_grad = len(_peer_grad)
+        for i, ptr in enumerate(_peer_grad):
+            a.peer_grad_ws[i] = int(ptr)
     with torch.cuda.device(dev):
         _check(lib.grpg_backward(C.byref(a)))
     if _stage == 1:

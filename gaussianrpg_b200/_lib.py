@@ -60,7 +60,7 @@ class BackwardArgs(C.Structure):
         ("dL_dmean3D", _fp), ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dscale", _fp), ("dL_drot", _fp),
         ("dL_dsemantic", _fp), ("grad_ws", _fp), ("stream", _fp),
         ("tile_row_stride", C.c_int), ("tile_row_phase", C.c_int), ("stages", C.c_int), ("p_begin", C.c_int),
-        ("p_count", C.c_int),
+        ("p_count", C.c_int), ("n_peer_grad", C.c_int), ("peer_grad_ws", _fp * 8),
     ]
 
 

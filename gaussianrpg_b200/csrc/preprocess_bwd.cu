@@ -16,6 +16,13 @@ namespace grpg {
 
 struct f3 { float x, y, z; };
 
+// Peer-mapped record buffers of all ranks (full size, global row index): the record all-reduce of the multi-GPU
+// backward is done here, in the load path of its only consumer.
+struct PeerGrad {
+    const float* p[8];
+    int n;
+};
+
 // Inputs are full-size arrays indexed by the global Gaussian id p_begin + i; grad_rec and every output hold
 // `P` rows for the slice [p_begin, p_begin + P) (row i).
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
@@ -24,7 +31,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     const float* __restrict__ rotations_full, float scale_modifier, const float* __restrict__ cov3Ds_full,
     const float* __restrict__ view, const float* __restrict__ proj, float h_x, float h_y, float tan_fovx,
     float tan_fovy, const float* __restrict__ campos, const float* __restrict__ grad_rec /*[P][12]*/,
-    float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic_out, float* __restrict__ dL_dopacity,
+    PeerGrad peers, float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic_out, float* __restrict__ dL_dopacity,
     float* __restrict__ dL_dcolor, float* __restrict__ dL_ddepth, float* __restrict__ dL_dmean3D,
     float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscale,
     float* __restrict__ dL_drot) {
@@ -42,9 +49,20 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     const bool vis = radii[idx] > 0;
 
     float4 g0 = make_float4(0, 0, 0, 0), g1 = g0, g2 = g0;
-    if (vis) {
+    if (vis && peers.n == 0) {
         const float4* gp = reinterpret_cast<const float4*>(grad_rec) + 3 * (size_t)idx;
         g0 = gp[0]; g1 = gp[1]; g2 = gp[2];
+    } else if (vis) {
+        // fixed summation order (rank 0, 1, ...) so that every rank obtains bit-identical sums
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r >= peers.n) break;
+            const float4* gp = reinterpret_cast<const float4*>(peers.p[r]) + 3 * (g0_ + (size_t)idx);
+            const float4 a0 = __ldcg(gp), a1 = __ldcg(gp + 1), a2 = __ldcg(gp + 2);
+            g0.x += a0.x; g0.y += a0.y; g0.z += a0.z; g0.w += a0.w;
+            g1.x += a1.x; g1.y += a1.y; g1.z += a1.z; g1.w += a1.w;
+            g2.x += a2.x; g2.y += a2.y; g2.z += a2.z; g2.w += a2.w;
+        }
     }
     // g0 = (dmean2D.x, dmean2D.y, |.|, dconic.x) g1 = (dconic.y, dconic.w, dopacity, dcolor.r) g2 = (dcolor.g, dcolor.b, ddepth, -)
     const float dm2x = g0.x, dm2y = g0.y, dm2abs = g0.z;
@@ -294,10 +312,13 @@ void launch_preprocess_bwd(const grpg_backward_args* a, const float* cov3D, cons
     if (P <= 0) return;
     const float focal_y = a->height / (2.0f * a->tan_fovy);
     const float focal_x = a->width / (2.0f * a->tan_fovx);
+    PeerGrad peers;
+    peers.n = a->n_peer_grad > 0 ? (a->n_peer_grad < 8 ? a->n_peer_grad : 8) : 0;
+    for (int r = 0; r < 8; ++r) peers.p[r] = r < peers.n ? a->peer_grad_ws[r] : nullptr;
     ProfScope ps("preprocess_bwd", stream);
     preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, a->p_begin, a->D, a->M, a->means3D, a->radii, a->shs, clamped, a->scales, a->rotations, a->scale_modifier, cov3D,
-        a->viewmatrix, a->projmatrix, focal_x, focal_y, a->tan_fovx, a->tan_fovy, a->cam_pos, grad_rec, a->dL_dmean2D,
+        a->viewmatrix, a->projmatrix, focal_x, focal_y, a->tan_fovx, a->tan_fovy, a->cam_pos, grad_rec, peers, a->dL_dmean2D,
         a->dL_dconic, a->dL_dopacity, a->dL_dcolor, a->dL_ddepth, a->dL_dmean3D, a->dL_dcov3D, a->dL_dsh, a->dL_dscale,
         a->dL_drot);
 }

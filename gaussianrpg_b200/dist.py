@@ -133,7 +133,35 @@ class _PeerFrame:
         return cls._cache[key]
 
 
+class _PeerRecords:
+    """Peer-mapped [P,12] gradient-record buffer: every rank's blend backward accumulates into its own copy, and
+    the per-Gaussian backward of every rank sums all copies in its load path (no separate all-reduce)."""
+    _cache = {}
+
+    def __init__(self, P: int, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rec = symm_mem.empty((P, 12), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.rec, group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    @classmethod
+    def get(cls, P, device, group):
+        key = (P, str(device), id(group))
+        if key not in cls._cache:
+            try:
+                cls._cache[key] = cls(P, device, group)
+            except Exception as exc:
+                cls._cache[key] = None
+                if dist.get_rank(group) == 0:
+                    print(f"[gaussianrpg_b200.dist] symmetric memory unavailable ({exc!r}); using NCCL all-reduce")
+        return cls._cache[key]
+
+
 FUSED_FORWARD_GATHER = True  # set False to force the NCCL all-gather path
+# Sum the gradient records inside the per-Gaussian backward (peer loads) for groups up to this size.  Reading
+# k-1 peers directly costs (k-1) x 48 B per visible Gaussian against 2(k-1)/k x 48 B per Gaussian for the ring
+# all-reduce, so the direct form only wins (fewer bytes, one kernel less, no extra pass over HBM) for small k.
+FUSED_RECORD_REDUCE_MAX_RANKS = 0
 
 
 # ---- the sharded operator --------------------------------------------------------------------------
@@ -187,9 +215,13 @@ class _ShardedRasterize(torch.autograd.Function):
         common = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                   rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy)
         tail = (sh, rs.sh_degree, rs.campos, geom, ctx.R, binning, img, alpha_b, semantics, rs.debug)
+        peer_rec = None
+        if (_EXCHANGE_PLAN == "replicate" and 1 < k <= FUSED_RECORD_REDUCE_MAX_RANKS and means3D.is_cuda
+                and dist.get_backend(group) == "nccl"):
+            peer_rec = _PeerRecords.get(P, means3D.device, group)
         grad_rec, g_semantics = _C.rasterize_gaussians_backward(
             *common, gb[:3].contiguous(), gb[3:4].contiguous(), gb[4:5].contiguous(), gb[5:5 + S].contiguous(), *tail,
-            _band=(k, r), _height=H, _width=W, _stage=1)
+            _band=(k, r), _height=H, _width=W, _stage=1, _grad_rec=peer_rec.rec if peer_rec is not None else None)
         # Sum the per-Gaussian 2D gradient records over ranks.  Two exchange plans:
         #  "shard":     reduce-scatter the 48 B records, per-Gaussian backward on the owned slice, all-gather the
         #               parameter-gradient shards (104 B per Gaussian for means/sh/opacity/scale/rotation);
@@ -198,10 +230,15 @@ class _ShardedRasterize(torch.autograd.Function):
         # "replicate" moves less than half the bytes and is the default; "shard" is what a ZeRO-style sharded
         # optimiser would use (it would simply skip the final all-gather).
         if _EXCHANGE_PLAN == "replicate":
-            dist.all_reduce(grad_rec, op=dist.ReduceOp.SUM, group=group)
+            if peer_rec is not None:
+                peer_rec.handle.barrier(channel=2)  # every rank's records are complete
+            else:
+                dist.all_reduce(grad_rec, op=dist.ReduceOp.SUM, group=group)
             shard = _C.rasterize_gaussians_backward(
                 *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _width=W, _stage=2,
-                _grad_rec=grad_rec, _slice=(0, P))
+                _grad_rec=grad_rec, _slice=(0, P), _peer_grad=peer_rec.ptrs if peer_rec is not None else None)
+            if peer_rec is not None:
+                peer_rec.handle.barrier(channel=3)  # nobody still reads this rank's records: they may be reused
             g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = shard[:8]
         else:
             Pp = padded_count(P, k)

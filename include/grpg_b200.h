@@ -198,6 +198,14 @@ typedef struct grpg_backward_args {
      * Between the stages a multi-GPU caller reduce-scatters grad_ws over the Gaussian axis. */
     int stages;
     int p_begin, p_count;
+    /* Fused record all-reduce over NVLink (multi-GPU, stage 2): when n_peer_grad > 0 the per-Gaussian backward
+     * ignores grad_ws and instead sums, in index order, the full-size [P][12] record buffers peer_grad_ws[0..n)
+     * (peer-mapped device pointers, this rank's own buffer included) while it loads them -- the reduction
+     * happens in the consumer's load path, there is no separate collective.  Only visible Gaussians are read.
+     * The caller orders the ranks: all stage-1 calls complete before any stage-2 call starts, and no buffer
+     * is reused before every rank's stage 2 has finished. */
+    int n_peer_grad;
+    const float* peer_grad_ws[8];
 } grpg_backward_args;
 
 size_t grpg_backward_workspace_bytes(int P, int S);

@@ -13,7 +13,10 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-sc_cpu = synthetic.street_scene(P=300000, W=1920, H=1066, n_actors=4, actor_points=5000, seed=3)
+if len(sys.argv) > 1 and sys.argv[1] == "full":
+    sc_cpu = synthetic.street_scene(P=2000000, W=1920, H=1280, seed=0)
+else:
+    sc_cpu = synthetic.street_scene(P=300000, W=1920, H=1066, n_actors=4, actor_points=5000, seed=3)
 sc = sc_cpu.to(dev)
 dL = [t.to(dev) for t in cases.loss_grads(sc_cpu)]
 
@@ -43,8 +46,20 @@ def fwd_ms(n=30):
     return e0.elapsed_time(e1) / n
 
 ref_out, ref_g = run(GaussianRasterizer)
-for fused in (True, False):
+def step_ms(n=20):
+    for _ in range(3):
+        run(ShardedGaussianRasterizer)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        run(ShardedGaussianRasterizer)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+for fused, fused_rec in ((True, True), (True, False), (False, False)):
     gdist.FUSED_FORWARD_GATHER = fused
+    gdist.FUSED_RECORD_REDUCE_MAX_RANKS = 8 if fused_rec else 0
     for rep in range(3):  # repeated: the peer frame is reused, so a missing barrier would show up as stale rows
         sh_out, sh_g = run(ShardedGaussianRasterizer)
     torch.cuda.synchronize()
@@ -53,9 +68,10 @@ for fused in (True, False):
     res = torch.tensor([0.0 if ok else 1.0, max(errs.values())], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     ms = fwd_ms()
+    sms = step_ms()
     if rank == 0:
-        print(f"fused_peer_store={fused} peer_frame={'yes' if any(v is not None for v in gdist._PeerFrame._cache.values()) else 'no'}:",
+        print(f"fused_peer_store={fused} fused_record_reduce={fused_rec} peer_frame={'yes' if any(v is not None for v in gdist._PeerFrame._cache.values()) else 'no'}:",
               "images bit-identical on all ranks:", float(res[0]) == 0.0, "max grad rel err: %.3g" % float(res[1]),
-              "sharded forward %.3f ms" % ms)
+              "sharded forward %.3f ms" % ms, "fwd+bwd (incl. leaf clones) %.3f ms" % sms)
 dist.barrier()
 dist.destroy_process_group()
