@@ -123,13 +123,16 @@ def make_step_fns(dgr, sc, gt, w_depth, w_alpha):
                                                       opacities=leaves["opacities"], shs=leaves["shs"],
                                                       scales=leaves["scales"], rotations=leaves["rotations"])
 
-    def fwd_bwd(view, proj, campos, gt_img):
+    def fwd_bwd(view, proj, campos, gt_img, gt_ready=None):
         for v in leaves.values():
             v.grad = None
         means2D = torch.zeros(P, 3, device=sc.means3D.device, requires_grad=True)
         color, radii, depth, alpha, _ = Rast(settings(view, proj, campos))(
             means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves["shs"],
             scales=leaves["scales"], rotations=leaves["rotations"])
+        if gt_ready is not None:  # the ground-truth image was uploaded on a side stream while the forward ran
+            torch.cuda.current_stream().wait_event(gt_ready)
+            gt_img.record_stream(torch.cuda.current_stream())
         # L1 image loss (train.py:116) + fixed-weight depth / accumulation terms so all three gradient inputs are live
         loss = (color - gt_img).abs().mean() + (depth * w_depth).mean() + (alpha * w_alpha).mean()
         loss.backward()
@@ -254,10 +257,18 @@ def main():
     ms_f = time_region(lambda: fwd_only(view, proj, campos), args.steps, False)
 
     # ---- end to end: per-step host inputs in, result out ---------------------------------------
+    # The camera is needed before the first kernel; the ground-truth image only by the loss, so its upload runs on
+    # a copy stream underneath the forward (what a prefetching data loader does).  Both arms use this protocol;
+    # every byte is still copied inside the timed region, every step.
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def e2e_fb():
         cam = cam_host.to(dev, non_blocking=True)
-        gt = gt_host.to(dev, non_blocking=True)
-        loss = fwd_bwd(cam[:16].view(4, 4), cam[16:32].view(4, 4), cam[32:35], gt)
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
+            gt = gt_host.to(dev, non_blocking=True)
+            gt_ready = copy_stream.record_event()
+        loss = fwd_bwd(cam[:16].view(4, 4), cam[16:32].view(4, 4), cam[32:35], gt, gt_ready)
         return float(loss.item())  # D2H read of the step's result
 
     img_host = torch.empty(3, H, W).pin_memory()
@@ -287,7 +298,8 @@ def main():
         _p = _dbg.parse_buffers(P, R, W, H, raw[6], raw[7], raw[8])
         _perm = bool((_p["sorted_idx"].long().sort().values == torch.arange(P, device=dev)).all())
         _sum = int(_p["tiles_touched"].long().sum())
-        base["index_check"] = {"R": R, "sum_tiles_touched": _sum, "depth_order_is_permutation": _perm,
+        base["index_check"] = {"R": R, "binned": _p["num_binned"], "sum_tiles_touched": _sum,
+                               "depth_order_is_permutation": _perm,
                                "keys_sorted": bool((_p["point_list_keys"][1:] >= _p["point_list_keys"][:-1]).all())}
 
     result = dict(base)
@@ -296,12 +308,13 @@ def main():
         fwd_fps=1000.0 * args.steps / ms_f, fwd_ms=ms_f / args.steps,
         e2e={"value": 1000.0 * args.steps / ms_e2e_fb, "unit": "iters/s",
              "h2d_bytes_per_step": int(cam_host.numel() * 4 + gt_host.numel() * 4), "d2h_bytes_per_step": 4,
-             "note": "camera (35 floats) + ground-truth image H2D from pinned memory, loss scalar D2H; Gaussian "
-                     "parameters are model state resident in HBM"},
+             "note": "camera (35 floats) + ground-truth image H2D from pinned memory (image upload on a copy stream, "
+                     "joined before the loss), loss scalar D2H; Gaussian parameters are model state resident in HBM"},
         e2e_fwd={"value": 1000.0 * args.steps / ms_e2e_f, "unit": "frames/s", "h2d_bytes_per_step": int(cam_host.numel() * 4),
                  "d2h_bytes_per_step": int(img_host.numel() * 4)},
         clocks={"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
-        config={"workload": workload, "P": P, "V": V, "R": R, "width": W, "height": H,
+        config={"workload": workload, "P": P, "V": V, "R": R,
+                "R_binned": base.get("index_check", {}).get("binned", R), "width": W, "height": H,
                 "l2": "no flush: one step streams > 126 MB (record table 48 B*P, 16 B*R instance lists, images)",
                 "timing": "CUDA events on the current stream around K steps after W warm-up steps"},
     )

@@ -55,8 +55,8 @@ def _layouts(P: int, R: int, W: int, H: int):
 
 def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
-                        degree, campos, prefiltered, debug, *, _band=(1, 0), _forward_only=False, _peer_frames=None
-                        ) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
+                        degree, campos, prefiltered, debug, *, _band=(1, 0), _forward_only=False, _peer_frames=None,
+                        _reference_binning=False) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
                                    torch.Tensor, torch.Tensor, torch.Tensor]:
     """RasterizeGaussiansCUDA (rasterize_points.cu:35-124).
 
@@ -65,7 +65,10 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
 
     `_band=(stride, phase)` (keyword-only, not part of the reference surface) restricts the call to the tile
     rows r with r % stride == phase; the images then use the compact band layout [C, rows*16, W]
-    (gaussianrpg_b200.dist reassembles them).
+    (gaussianrpg_b200.dist reassembles them).  `_reference_binning=True` bins exactly the reference's tile
+    rectangles (index buffers then equal the reference's element for element); by default rectangles are clipped
+    to the alpha >= 1/255 footprint, which drops instances the reference sorts and then skips.  `num_rendered` is
+    the reference's count either way.
     """
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:58-60
@@ -130,20 +133,21 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
     a.stream = _stream()
     a.tile_row_stride, a.tile_row_phase = stride, phase
     a.forward_only = int(bool(_forward_only))
+    a.reference_binning = int(bool(_reference_binning))
     if _peer_frames:
         a.n_peer_frames = len(_peer_frames)
         for i, ptr in enumerate(_peer_frames):
             a.peer_frames[i] = int(ptr)
 
     with torch.cuda.device(dev):
-        n = C.c_int(0)
-        _check(lib.grpg_forward_geometry(C.byref(a), C.byref(n)))
-        R = int(n.value)
+        n_binned, n_rendered = C.c_int(0), C.c_int(0)
+        _check(lib.grpg_forward_geometry(C.byref(a), C.byref(n_binned), C.byref(n_rendered)))
         bl = _lib.BinningLayout()
-        lib.grpg_get_binning_layout(R, C.byref(bl))
-        binning = torch.empty(bl.total_bytes if R > 0 else 0, **u8)
+        lib.grpg_get_binning_layout(int(n_binned.value), C.byref(bl))
+        binning = torch.empty(max(int(bl.total_bytes), 256), **u8)  # never empty: backward needs a valid pointer
         a.binning_ws = _ptr(binning)
-        _check(lib.grpg_forward_render(C.byref(a), R))
+        _check(lib.grpg_forward_render(C.byref(a), int(n_binned.value)))
+    R = int(n_rendered.value)
     return R, out_color, out_depth, out_alpha, out_semantic, radii, geom, binning, img
 
 

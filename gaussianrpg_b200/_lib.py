@@ -41,7 +41,7 @@ class ForwardArgs(C.Structure):
         ("viewmatrix", _fp), ("projmatrix", _fp), ("cam_pos", _fp),
         ("out_color", _fp), ("out_depth", _fp), ("out_alpha", _fp), ("out_semantic", _fp), ("radii", _fp),
         ("geom_ws", _fp), ("binning_ws", _fp), ("image_ws", _fp), ("stream", _fp),
-        ("tile_row_stride", C.c_int), ("tile_row_phase", C.c_int), ("forward_only", C.c_int),
+        ("tile_row_stride", C.c_int), ("tile_row_phase", C.c_int), ("forward_only", C.c_int), ("reference_binning", C.c_int),
         ("n_peer_frames", C.c_int), ("peer_frames", _fp * 8),
     ]
 
@@ -71,7 +71,7 @@ SYMBOLS = {
     "grpg_get_image_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(ImageLayout)]),
     "grpg_band_rows": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "grpg_band_height": (C.c_int, [C.c_int, C.c_int, C.c_int]),
-    "grpg_forward_geometry": (C.c_int, [C.POINTER(ForwardArgs), C.POINTER(C.c_int)]),
+    "grpg_forward_geometry": (C.c_int, [C.POINTER(ForwardArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "grpg_forward_render": (C.c_int, [C.POINTER(ForwardArgs), C.c_int]),
     "grpg_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "grpg_backward": (C.c_int, [C.POINTER(BackwardArgs)]),

@@ -9,7 +9,7 @@ namespace grpg {
 // preprocess_fwd.cu
 void launch_preprocess_fwd(const grpg_forward_args* a, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
                            Rec* rec, uint32_t* depth_key, uint2* rect, uint32_t* tiles_touched, float* cov3d,
-                           uint8_t* clamped, cudaStream_t stream);
+                           uint8_t* clamped, unsigned long long* ref_instances, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
 void launch_visible_filter(int P, int W, int H, const float* means3D, const float* scales, float scale_modifier,
                            const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
@@ -18,6 +18,7 @@ void launch_visible_filter(int P, int W, int H, const float* means3D, const floa
 // binning.cu
 size_t geom_scratch_bytes(int P);
 size_t binning_scratch_bytes(long long R);
+unsigned long long* prepare_geometry_scratch(int P, void* scratch, cudaStream_t stream);
 void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, const uint32_t* tiles_touched,
                               uint32_t* offsets, void* scratch, unsigned long long* num_rendered_dev, int num_sms,
                               cudaStream_t stream);
@@ -147,7 +148,7 @@ int grpg_get_geometry_layout(int P, grpg_geom_layout* out) {
     out->sorted_idx = take(p * 4);
     out->offsets = take(p * 4);
     out->scratch = take(geom_scratch_bytes(P));
-    out->num_rendered = take(8);
+    out->num_rendered = take(16);
     out->total_bytes = o;
     return 0;
 }
@@ -197,9 +198,10 @@ static int validate_forward(const grpg_forward_args* a) {
     return 0;
 }
 
-int grpg_forward_geometry(const grpg_forward_args* a, int* num_rendered) {
-    if (!num_rendered) return fail("null num_rendered");
-    *num_rendered = 0;
+int grpg_forward_geometry(const grpg_forward_args* a, int* num_binned, int* num_rendered) {
+    if (!num_binned) return fail("null num_binned");
+    *num_binned = 0;
+    if (num_rendered) *num_rendered = 0;
     if (int rc = validate_forward(a)) return rc;
     if (a->P == 0) return 0;
     cudaStream_t stream = (cudaStream_t)a->stream;
@@ -209,18 +211,20 @@ int grpg_forward_geometry(const grpg_forward_args* a, int* num_rendered) {
     const float focal_y = a->height / (2.0f * a->tan_fovy);
     const float focal_x = a->width / (2.0f * a->tan_fovx);
     const uint32_t gx = (a->width + 15) / 16, gy = (a->height + 15) / 16;
+    unsigned long long* ref_instances = prepare_geometry_scratch(a->P, g + L.scratch, stream);
     launch_preprocess_fwd(a, focal_x, focal_y, gx, gy, (Rec*)(g + L.rec), (uint32_t*)(g + L.depth_key),
                           (uint2*)(g + L.rect), (uint32_t*)(g + L.tiles_touched), (float*)(g + L.cov3d),
-                          (uint8_t*)(g + L.clamped), stream);
+                          (uint8_t*)(g + L.clamped), ref_instances, stream);
     if (a->debug) if (int rc = check_cuda("preprocess", true, stream)) return rc;
     run_depth_order_and_scan(a->P, (uint32_t*)(g + L.depth_key), (uint32_t*)(g + L.sorted_idx),
                              (const uint32_t*)(g + L.tiles_touched), (uint32_t*)(g + L.offsets), g + L.scratch,
                              (unsigned long long*)(g + L.num_rendered), device_sm_count(), stream);
     unsigned long long* host = pinned_word();
-    cudaMemcpyAsync(host, g + L.num_rendered, 8, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(host, g + L.num_rendered, 16, cudaMemcpyDeviceToHost, stream);
     if (int rc = check_cuda("forward_geometry", true, stream)) return rc;
-    if (*host >= (1ull << 30)) return fail("too many Gaussian/tile instances (>= 2^30)");
-    *num_rendered = (int)*host;
+    if (host[0] >= (1ull << 30) || host[1] >= (1ull << 31)) return fail("too many Gaussian/tile instances (>= 2^30)");
+    *num_binned = (int)host[0];
+    if (num_rendered) *num_rendered = (int)host[1];
     return 0;
 }
 
@@ -283,7 +287,7 @@ int grpg_backward(const grpg_backward_args* a_in) {
         cudaMemsetAsync(grad_rec, 0, (size_t)a->P * 12 * sizeof(float), stream);
         if (a->S > 0) cudaMemsetAsync(a->dL_dsemantic, 0, (size_t)a->P * a->S * sizeof(float), stream);
         if (a->R > 0) {
-            if (!b) return fail("missing binning workspace");
+            if (!b) return fail("missing binning workspace");  // allocate >= 16 bytes even when nothing was binned
             launch_blend_bwd(a, (const uint2*)(im + IL.ranges), (const uint32_t*)(b + BL.point_list),
                              (const Rec*)(g + L.rec), (const uint32_t*)(im + IL.n_contrib), grad_rec, stream);
             if (a->debug) if (int rc = check_cuda("blend backward", true, stream)) return rc;

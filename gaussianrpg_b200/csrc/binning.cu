@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
                                                          unsigned long long* __restrict__ status /*[tiles+1]*/,
                                                          uint32_t* __restrict__ tile_counter,
                                                          unsigned long long* __restrict__ total_out,
+                                                         const unsigned long long* __restrict__ ref_instances,
                                                          uint32_t* __restrict__ chunk_start) {
     __shared__ uint32_t s_scan[8];
     __shared__ uint32_t s_tile;
@@ -86,7 +87,10 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
         if (lane == 0) {
             if (tile > 0) st_volatile_u64(status + tile, (excl + block_total) | SC_FLAG_PREFIX);
             s_excl = excl;
-            if ((tile + 1) * (unsigned long long)SCAN_TILE >= P) *total_out = excl + block_total;
+            if ((tile + 1) * (unsigned long long)SCAN_TILE >= P) {
+                total_out[0] = excl + block_total;  // instances to bin
+                total_out[1] = *ref_instances;       // instances the reference would bin (its num_rendered)
+            }
         }
     }
     __syncthreads();
@@ -233,6 +237,21 @@ size_t binning_scratch_bytes(long long R) {
     return b;
 }
 
+// offset of the [scan status | counters] block inside the geometry scratch
+static size_t geom_status_offset(int P) {
+    return align_up((size_t)P * 4, 256) * 2 +
+           align_up((size_t)SORT_MAX_PASSES * (256 + 64) * 4 + (size_t)SORT_MAX_PASSES * sort_num_tiles(P) * 256 * 4, 256);
+}
+// Zeroes the scan status words and the counters (before the projection kernel, which accumulates the reference's
+// instance count into the returned counter).
+unsigned long long* prepare_geometry_scratch(int P, void* scratch, cudaStream_t stream) {
+    char* p = (char*)scratch + geom_status_offset(P);
+    const size_t scan_tiles = ((size_t)P + SCAN_TILE - 1) / SCAN_TILE;
+    const size_t status_bytes = align_up((scan_tiles + 2) * 8, 256);
+    cudaMemsetAsync(p, 0, status_bytes + 256, stream);
+    return (unsigned long long*)(p + status_bytes + 64);  // counters block: [0] scan tile ticket, [64] ref instances
+}
+
 // Steps 1-2.  depth_key is consumed (left sorted); sorted_idx receives the permutation.
 void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, const uint32_t* tiles_touched,
                               uint32_t* offsets, void* scratch, unsigned long long* num_rendered_dev, int num_sms,
@@ -257,10 +276,11 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
         cudaMemcpyAsync(depth_key, keys_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(sorted_idx, vals_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
     }
-    cudaMemsetAsync(status, 0, (scan_tiles + 2) * 8 + 256, stream);
+    // status words and counters were zeroed by prepare_geometry_scratch
     ProfScope ps("scan_tiles", stream);
-    scan_tiles_kernel<<<(unsigned)scan_tiles, 256, 0, stream>>>(sorted_idx, tiles_touched, (uint32_t)P, offsets, status,
-                                                                 scan_counter, num_rendered_dev, chunk_start);
+    scan_tiles_kernel<<<(unsigned)scan_tiles, 256, 0, stream>>>(
+        sorted_idx, tiles_touched, (uint32_t)P, offsets, status, scan_counter, num_rendered_dev,
+        (const unsigned long long*)((const char*)scan_counter + 64), chunk_start);
 }
 
 // Steps 3-5.  Final order lands in (tile_keys, point_list).

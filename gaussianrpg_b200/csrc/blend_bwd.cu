@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     __shared__ __align__(16) float4 s_rec[BWD_BATCH * 3];  // staged records, 48-byte stride
     __shared__ uint32_t s_id[BWD_BATCH];
     __shared__ int s_maxlast[8];
-    __shared__ uint16_t s_q[8][BWD_BATCH];  // per-warp queue of surviving slots, as byte offsets (slot * 48)
+    __shared__ uint16_t s_q[8][BWD_BATCH];  // per-warp queue of surviving staged slots
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
@@ -141,16 +141,15 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
             // slots whose position lies behind every pixel's last contributor cannot receive gradient
             const bool hit = j < cnt && (top - 1 - j) < wmax && footprint_hits_exact(s_rec[3 * j], s_rec[3 * j + 1], bx_lo, bx_hi, by_lo, by_hi);
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(j * 48);
+            if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
             n_q += __popc(m);
         }
         __syncwarp();
         // phase 2: back-to-front replay of the survivors
         {
             for (int qi = 0; qi < n_q; ++qi) {
-                const uint32_t off = q[qi];
-                const int k = (int)(off / 48u);
-                const float4* rk = reinterpret_cast<const float4*>(rec_base + off);
+                const int k = (int)q[qi];
+                const float4* rk = reinterpret_cast<const float4*>(rec_base + (uint32_t)k * 48u);
                 const int pos = top - 1 - k;  // 0-based position in the tile's range
                 const float4 a = rk[0];
                 const float4 b = rk[1];

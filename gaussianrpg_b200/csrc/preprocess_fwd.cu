@@ -237,8 +237,10 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
     int prefiltered, int row_stride, int row_phase, int forward_only, int* __restrict__ radii, Rec* __restrict__ rec, uint32_t* __restrict__ depth_key,
     uint2* __restrict__ rect, uint32_t* __restrict__ tiles_touched, float* __restrict__ cov3D_out,
-    uint8_t* __restrict__ clamped) {
+    uint8_t* __restrict__ clamped, int reference_binning, unsigned long long* __restrict__ ref_instances) {
     __shared__ float s_cam[35];
+    __shared__ uint32_t s_ref_count;  // instances the reference bins for this CTA's Gaussians (its num_rendered)
+    if (threadIdx.x == 0) s_ref_count = 0;
     // Per-CTA slices of the AoS attribute arrays are contiguous in global memory (256 x 12 B means, 256 x 12 B
     // scales, 256 x 48 B SH at M = 4), so they are staged with TMA bulk copies (one elected thread, one mbarrier)
     // and then read conflict-free from shared memory -- instead of 12-byte-strided per-thread loads.
@@ -304,6 +306,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
         vis = o.visible;
     }
     Rec r;
+    uint32_t ref_count = 0;
     if (!vis) {
         radii[idx] = 0;
         tiles_touched[idx] = 0;
@@ -326,34 +329,66 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
         r.b = make_float4(o.conx, o.cony, o.conz, opacity);
         r.c = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
         radii[idx] = o.radius;
-        uint32_t ly0 = o.ymin, ly1 = o.ymax;
-        if (row_stride > 1) {
-            // rows of [ymin, ymax) owned by this band (r % stride == phase), expressed as local row indices
-            const uint32_t st = (uint32_t)row_stride, ph = (uint32_t)row_phase;
-            const uint32_t first = o.ymin + ((ph + st - o.ymin % st) % st);
-            if (first < o.ymax) { ly0 = (first - ph) / st; ly1 = ly0 + (o.ymax - 1 - first) / st + 1; }
-            else { ly0 = 0; ly1 = 0; }
+        // rows of [y0, y1) owned by this band (row % stride == phase), expressed as local row indices
+        auto band_clip = [&](uint32_t y0, uint32_t y1, uint32_t& l0, uint32_t& l1) {
+            l0 = y0; l1 = y1;
+            if (row_stride > 1) {
+                const uint32_t st = (uint32_t)row_stride, ph = (uint32_t)row_phase;
+                const uint32_t first = y0 + ((ph + st - y0 % st) % st);
+                if (first < y1) { l0 = (first - ph) / st; l1 = l0 + (y1 - 1 - first) / st + 1; }
+                else { l0 = 0; l1 = 0; }
+            }
+        };
+        uint32_t ly0, ly1;
+        band_clip(o.ymin, o.ymax, ly0, ly1);
+        ref_count = (o.xmax - o.xmin) * (ly1 - ly0);  // what the reference bins: getRect of the 3-sigma radius
+        uint32_t bx0 = o.xmin, bx1 = o.xmax;
+        if (!reference_binning && !(hx == __int_as_float(0x7f800000))) {
+            // Clip the rectangle to the tiles that hold a pixel with |dx| <= hx and |dy| <= hy: outside, alpha is
+            // provably < 1/255 and the reference's blend skips the pair (forward.cu:418-426), so the instance is
+            // never binned.  Images, gradients and radii are unchanged; the instance lists become the reference's
+            // lists minus those dead entries.
+            uint32_t by0 = o.ymin, by1 = o.ymax;
+            if (hx < 0.0f || hy < 0.0f) {
+                bx1 = bx0; by1 = by0;
+            } else {
+                const double xl = floor(((double)o.px - (double)hx) * 0.0625), xh = floor(((double)o.px + (double)hx) * 0.0625) + 1.0;
+                const double yl = floor(((double)o.py - (double)hy) * 0.0625), yh = floor(((double)o.py + (double)hy) * 0.0625) + 1.0;
+                bx0 = (uint32_t)fmin(fmax(xl, (double)o.xmin), (double)o.xmax);
+                bx1 = (uint32_t)fmax(fmin(xh, (double)o.xmax), (double)bx0);
+                by0 = (uint32_t)fmin(fmax(yl, (double)o.ymin), (double)o.ymax);
+                by1 = (uint32_t)fmax(fmin(yh, (double)o.ymax), (double)by0);
+            }
+            band_clip(by0, by1, ly0, ly1);
         }
-        tiles_touched[idx] = (o.xmax - o.xmin) * (ly1 - ly0);
+        tiles_touched[idx] = (bx1 - bx0) * (ly1 - ly0);
         depth_key[idx] = __float_as_uint(o.depth);
-        rect[idx] = make_uint2(o.xmin | (o.xmax << 16), ly0 | (ly1 << 16));
+        rect[idx] = make_uint2(bx0 | (bx1 << 16), ly0 | (ly1 << 16));
     }
     // The 256 records of a full CTA are one contiguous 12 KB range: each thread drops its record into its own
     // (already consumed) 48-byte SH slot and one thread writes the range back with a TMA bulk store.
     if (full_cta) {
+        ref_count = __reduce_add_sync(0xffffffffu, ref_count);
+        if ((threadIdx.x & 31) == 0 && ref_count) atomicAdd(&s_ref_count, ref_count);
         float4* slot = reinterpret_cast<float4*>(s_sh) + 3 * threadIdx.x;
         slot[0] = r.a; slot[1] = r.b; slot[2] = r.c;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 0) {
+            if (s_ref_count) atomicAdd(ref_instances, (unsigned long long)s_ref_count);
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rec + cta_first),
                          "r"(smem_u32(s_sh)), "r"(256u * 48u)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-    } else if (vis) {
-        rec[idx] = r;
+    } else {
+        if (vis) rec[idx] = r;
+        // ragged / misaligned CTAs (threads past P have exited): warp-aggregated instead of CTA-aggregated
+        const unsigned active = __activemask();
+        ref_count = __reduce_add_sync(active, ref_count);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(active) - 1) && ref_count)
+            atomicAdd(ref_instances, (unsigned long long)ref_count);
     }
 }
 
@@ -400,13 +435,14 @@ __global__ void __launch_bounds__(256) visible_filter_kernel(
 
 void launch_preprocess_fwd(const grpg_forward_args* a, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
                            Rec* rec, uint32_t* depth_key, uint2* rect, uint32_t* tiles_touched, float* cov3d,
-                           uint8_t* clamped, cudaStream_t stream) {
+                           uint8_t* clamped, unsigned long long* ref_instances, cudaStream_t stream) {
     const int P = a->P;
     ProfScope ps("preprocess_fwd", stream);
     preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs, a->cov3D_precomp,
         a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos, a->width, a->height, a->tan_fovx, a->tan_fovy,
-        focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->tile_row_stride, a->tile_row_phase, a->forward_only, a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped);
+        focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->tile_row_stride, a->tile_row_phase, a->forward_only, a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped,
+        a->reference_binning, ref_instances);
 }
 
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream) {

@@ -20,9 +20,17 @@ def _view(buf: torch.Tensor, offset: int, count: int, dtype: torch.dtype) -> tor
 
 
 def parse_buffers(P: int, R: int, W: int, H: int, geom: torch.Tensor, binning: torch.Tensor, img: torch.Tensor):
+    """`R` (the num_rendered returned by the forward) is only a fallback: the number of binned instances, which
+    sizes the binning buffer, is read from the geometry buffer (it is smaller than num_rendered unless the
+    forward ran with `_reference_binning=True`)."""
     lib = _lib.load()
     gl, bl, il = _lib.GeomLayout(), _lib.BinningLayout(), _lib.ImageLayout()
     lib.grpg_get_geometry_layout(P, C.byref(gl))
+    if P > 0:
+        counts = _view(geom, gl.num_rendered, 2, torch.int64).cpu()
+        num_rendered, R = int(counts[1]), int(counts[0])
+    else:
+        num_rendered = R
     lib.grpg_get_binning_layout(R, C.byref(bl))
     lib.grpg_get_image_layout(W, H, C.byref(il))
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
@@ -37,6 +45,7 @@ def parse_buffers(P: int, R: int, W: int, H: int, geom: torch.Tensor, binning: t
         rect_max=torch.stack([(rect[:, 0] >> 16) & 0xFFFF, (rect[:, 1] >> 16) & 0xFFFF], 1),
         n_contrib=_view(img, il.n_contrib, W * H, torch.int32).view(H, W),
         ranges=_view(img, il.ranges, tiles * 2, torch.int32).view(tiles, 2),
+        num_binned=R, num_rendered=num_rendered,
     )
     if R > 0:
         out["point_list"] = _view(binning, bl.point_list, R, torch.int32)

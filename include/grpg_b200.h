@@ -39,14 +39,14 @@ typedef struct grpg_geom_layout {
     size_t total_bytes;
     size_t rec;            /* float4[3*P]: (x,y,hx,hy) (A,B,C,opacity) (r,g,b,depth)        */
     size_t depth_key;      /* uint32[P]: float bits of view depth, 0xFFFFFFFF if culled     */
-    size_t rect;           /* uint32[2*P]: xmin | xmax<<16, ymin | ymax<<16                 */
-    size_t tiles_touched;  /* uint32[P]                                                     */
+    size_t rect;           /* uint32[2*P]: xmin | xmax<<16, ymin | ymax<<16 of the BINNED rectangle */
+    size_t tiles_touched;  /* uint32[P]: tiles of the binned rectangle                      */
     size_t cov3d;          /* float[6*P]                                                    */
     size_t clamped;        /* uint8[P]: bit c set when SH colour channel c was clamped      */
     size_t sorted_idx;     /* uint32[P]: Gaussian ids ordered by (depth bits, id)           */
     size_t offsets;        /* uint32[P]: exclusive scan of tiles_touched in sorted order    */
     size_t scratch;        /* sort ping-pong buffers, histograms, look-back state           */
-    size_t num_rendered;   /* uint32[1] device copy of R                                    */
+    size_t num_rendered;   /* uint64[2] device copies of (num_binned, num_rendered)         */
 } grpg_geom_layout;
 
 typedef struct grpg_binning_layout {
@@ -118,6 +118,14 @@ typedef struct grpg_forward_args {
     /* non-zero: no backward will follow (inference): the per-Gaussian cov3D / SH-clamp state that only
      * grpg_backward reads is not written (saves 25 B per visible Gaussian of HBM writes) */
     int forward_only;
+    /* Binning rectangle.  0 (default): the reference's rectangle (getRect of the 3-sigma radius,
+     * auxiliary.h:46-60) clipped to the tiles that contain a pixel where alpha can reach 1/255 for the stored
+     * conic/opacity; everything outside is an instance the reference bins, sorts and then skips in the blend
+     * (forward.cu:418-426).  Images, radii and gradients are identical; the instance list is the reference's
+     * list minus those dead entries (same relative order).  1: bin exactly the reference's rectangle, so that
+     * tiles_touched / point_list / ranges / n_contrib equal the reference's buffers element for element
+     * (used by the index-parity tests and for debugging). */
+    int reference_binning;
     /* Fused band all-gather over NVLink (multi-GPU, with tile_row_stride > 1): when n_peer_frames > 0 the blend
      * kernel also stores every pixel of its band straight into each peer's FULL frame
      * peer_frames[i] = float[(5 + S), H, W] (channels: 0-2 colour, 3 depth, 4 alpha, 5.. semantics), addressed
@@ -133,16 +141,18 @@ int grpg_band_rows(int height, int stride, int phase);
 int grpg_band_height(int height, int stride, int phase);
 
 /* Stage 1: projection (preprocessCUDA forward.cu:155-256), depth ordering and the
- * prefix sum of tile counts (rasterizer_impl.cu:280).  Writes R to *num_rendered
- * (host) after synchronising `stream` -- the one host sync of the forward path
- * (reference: rasterizer_impl.cu:284). */
-int grpg_forward_geometry(const grpg_forward_args* a, int* num_rendered);
+ * prefix sum of tile counts (rasterizer_impl.cu:280).  After synchronising `stream` -- the one host sync of
+ * the forward path (reference: rasterizer_impl.cu:284) -- writes to the host
+ *   *num_binned   = instances this library bins (sizes grpg_get_binning_layout, pass it to grpg_forward_render),
+ *   *num_rendered = instances the reference bins = the `num_rendered` RasterizeGaussiansCUDA returns
+ *                   (may be NULL; equals *num_binned when reference_binning != 0). */
+int grpg_forward_geometry(const grpg_forward_args* a, int* num_binned, int* num_rendered);
 
 /* Stage 2: instance emission (duplicateWithKeys rasterizer_impl.cu:70-111), the
  * (tile | depth | id) ordering (SortPairs rasterizer_impl.cu:306-311), tile ranges
  * (identifyTileRanges :116-138) and the per-tile front-to-back blend (renderCUDA
  * forward.cu:340-467). */
-int grpg_forward_render(const grpg_forward_args* a, int num_rendered);
+int grpg_forward_render(const grpg_forward_args* a, int num_binned);
 
 /* ------------------------------------------------------------------------- */
 /* Backward.  Replaces CudaRasterizer::Rasterizer::backward                   */

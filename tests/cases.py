@@ -89,8 +89,9 @@ def oracle_run(sc, with_backward=True):
     return pre, binned, img, grads
 
 
-def raw_forward(mod_C, sc, debug=False):
-    """Call a `_C`-style module (ours or the reference's) with a Scene already on the GPU."""
+def raw_forward(mod_C, sc, debug=False, **kw):
+    """Call a `_C`-style module (ours or the reference's) with a Scene already on the GPU; `kw` = our
+    keyword-only extras (e.g. `_reference_binning=True`)."""
     E = torch.Tensor([])
     P = sc.means3D.shape[0]
     sem = sc.semantics if sc.semantics is not None else torch.zeros(P, 0, device=sc.means3D.device)
@@ -98,7 +99,7 @@ def raw_forward(mod_C, sc, debug=False):
     return mod_C.rasterize_gaussians(sc.bg, sc.means3D, opt(sc.colors_precomp), sem, sc.opacities, opt(sc.scales),
                                      opt(sc.rotations), sc.scale_modifier, opt(sc.cov3D_precomp), sc.viewmatrix,
                                      sc.projmatrix, sc.tanfovx, sc.tanfovy, sc.height, sc.width, opt(sc.shs),
-                                     sc.sh_degree, sc.campos, False, debug)
+                                     sc.sh_degree, sc.campos, False, debug, **kw)
 
 
 def raw_backward(mod_C, sc, fwd, dL, debug=False):

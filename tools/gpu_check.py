@@ -22,7 +22,8 @@ def run_both(sc, S_grad=True, label=""):
                 sc.cov3D_precomp if sc.cov3D_precomp is not None else E, sc.viewmatrix, sc.projmatrix, sc.tanfovx, sc.tanfovy,
                 H, W, sc.shs if sc.shs is not None else E, sc.sh_degree, sc.campos, False, False)
     torch.cuda.synchronize()
-    o = _C.rasterize_gaussians(*args()); torch.cuda.synchronize()
+    o = _C.rasterize_gaussians(*args(), _reference_binning=True); torch.cuda.synchronize()
+    op = _C.rasterize_gaussians(*args()); torch.cuda.synchronize()  # product default: clipped rectangles
     r = ref._C.rasterize_gaussians(*args()); torch.cuda.synchronize()
     Ro, Rr = o[0], r[0]
     res = dict(label=label or sc.name, P=P, R_ours=Ro, R_ref=Rr)
@@ -31,6 +32,9 @@ def run_both(sc, S_grad=True, label=""):
             res[f"maxabs_{name}"] = float((o[i] - r[i]).abs().max())
             res[f"neq_{name}"] = int((o[i] != r[i]).sum())
     res["neq_radii"] = int((o[5] != r[5]).sum())
+    res["product_path"] = dict(num_rendered=op[0], neq_color=int((op[1] != r[1]).sum()), neq_depth=int((op[2] != r[2]).sum()),
+                               neq_alpha=int((op[3] != r[3]).sum()),
+                               binned=debug.parse_buffers(P, op[0], W, H, op[6], op[7], op[8])["num_binned"])
     mine = debug.parse_buffers(P, Ro, W, H, o[6], o[7], o[8])
     theirs = parse_reference(P, Rr, W, H, r[6], r[7], r[8])
     vis = r[5] > 0
@@ -54,7 +58,7 @@ def run_both(sc, S_grad=True, label=""):
                 sc.scales if sc.scales is not None else E, sc.rotations if sc.rotations is not None else E, sc.scale_modifier,
                 sc.cov3D_precomp if sc.cov3D_precomp is not None else E, sc.viewmatrix, sc.projmatrix, sc.tanfovx, sc.tanfovy,
                 dc, dd, da, ds, sc.shs if sc.shs is not None else E, sc.sh_degree, sc.campos, t[6], t[0], t[7], t[8], t[3], sem, False)
-    go = _C.rasterize_gaussians_backward(*bargs(o)); torch.cuda.synchronize()
+    go = _C.rasterize_gaussians_backward(*bargs(op)); torch.cuda.synchronize()
     gr = ref._C.rasterize_gaussians_backward(*bargs(r)); torch.cuda.synchronize()
     names = ["dmeans2D", "dcolors", "dopacity", "dmeans3D", "dcov3D", "dsh", "dscales", "drot", "dsem"]
     for n, a, b in zip(names, go, gr):
@@ -69,7 +73,7 @@ def run_both(sc, S_grad=True, label=""):
         e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n
     res["ms_fwd_ours"] = timeit(lambda: _C.rasterize_gaussians(*args()))
     res["ms_fwd_ref"] = timeit(lambda: ref._C.rasterize_gaussians(*args()))
-    res["ms_bwd_ours"] = timeit(lambda: _C.rasterize_gaussians_backward(*bargs(o)))
+    res["ms_bwd_ours"] = timeit(lambda: _C.rasterize_gaussians_backward(*bargs(op)))
     res["ms_bwd_ref"] = timeit(lambda: ref._C.rasterize_gaussians_backward(*bargs(r)))
     print(json.dumps(res), flush=True)
     return res
