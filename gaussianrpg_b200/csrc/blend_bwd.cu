@@ -63,8 +63,10 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dalphas,
     const float* __restrict__ dL_dpixel_semantics, float* __restrict__ grad_rec /*[P][12]*/,
     float* __restrict__ dL_dsemantics /*[P][S]*/, int HL, int row_stride, int row_phase) {
-    __shared__ __align__(16) float4 s_rec[BWD_BATCH * 3];  // staged records, 48-byte stride
-    __shared__ uint32_t s_id[BWD_BATCH];
+    // staged records (48-byte stride) and ids, double buffered and filled one batch ahead with cp.async
+    // (see blend_fwd.cu)
+    __shared__ __align__(16) float4 s_rec2[2][BWD_BATCH * 3];
+    __shared__ uint32_t s_id2[2][BWD_BATCH];
     __shared__ int s_maxlast[8];
     __shared__ uint16_t s_q[8][BWD_BATCH];  // per-warp queue of surviving staged slots
 
@@ -117,19 +119,29 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     for (int w = 0; w < 8; ++w) tile_last = max(tile_last, s_maxlast[w]);
     tile_last = min(tile_last, n_inst);
 
-    for (int top = tile_last; top > 0; top -= BWD_BATCH) {
-        const int cnt = min(BWD_BATCH, top);
-        __syncthreads();
-        if (tid < cnt) {
-            // slot t holds 0-based position top-1-t: ascending slot = back-to-front
-            const uint32_t id = point_list[range.x + top - 1 - tid];
+    // slot t of the batch that starts at `top` holds 0-based position top-1-t: ascending slot = back-to-front
+    auto stage = [&](int buf, int top, uint32_t id) {
+        if (top - 1 - tid >= 0) {
             const float4* r = reinterpret_cast<const float4*>(rec + id);
-            s_rec[3 * tid] = __ldg(r);
-            s_rec[3 * tid + 1] = __ldg(r + 1);
-            s_rec[3 * tid + 2] = __ldg(r + 2);
-            s_id[tid] = id;
+            float4* d = &s_rec2[buf][3 * tid];
+            cp_async16(d, r); cp_async16(d + 1, r + 1); cp_async16(d + 2, r + 2);
+            s_id2[buf][tid] = id;
         }
-        __syncthreads();
+        cp_async_commit();
+    };
+    auto fetch_id = [&](int top) { return top - 1 - tid >= 0 ? point_list[range.x + top - 1 - tid] : 0u; };
+    uint32_t id_next = fetch_id(tile_last);
+    stage(0, tile_last, id_next);
+    id_next = fetch_id(tile_last - BWD_BATCH);
+
+    for (int top = tile_last, it = 0; top > 0; top -= BWD_BATCH, ++it) {
+        const int cnt = min(BWD_BATCH, top);
+        cp_async_wait_all();
+        __syncthreads();  // batch `it` has landed for everyone, and every warp has left batch it-1
+        const float4* s_rec = s_rec2[it & 1];
+        const uint32_t* s_id = s_id2[it & 1];
+        stage((it + 1) & 1, top - BWD_BATCH, id_next);
+        id_next = fetch_id(top - 2 * BWD_BATCH);
         if (wmax <= top - cnt) continue;  // every pixel of this warp ended before this batch
 
         // phase 1: footprint test of the whole batch, survivors compacted into a per-warp byte queue
@@ -237,6 +249,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
             }
         }
     }
+    cp_async_wait_all();  // nothing may be in flight into shared memory when the CTA retires
 }
 
 void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const uint32_t* point_list, const Rec* rec,
