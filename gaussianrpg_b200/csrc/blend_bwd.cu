@@ -23,34 +23,28 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Sums 16 per-lane values over the warp with 16 shuffles instead of 80: at every butterfly step a
-// lane hands half of its remaining slots to its partner and keeps the other half, so after the
-// xor-16/8/4/2 steps each lane owns ONE slot and the xor-1 step completes it.  On return the lane
-// holds the warp total of slot ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1).
-__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
-    float a[8], b[4], c[2];
+// Sums 12 per-lane values over the warp with 13 shuffles instead of 60: at every butterfly step a lane hands
+// half of its remaining slots to its partner and keeps the other half (12 -> 6 -> 3(+1 pad) -> 2 -> 1), and
+// the xor-1 step completes the one slot the lane is left with.  On return the lane holds the warp total of
+// slot 6*b4 + 3*b3 + (2*b2 + b1) (b_k = bit k of the lane id); lanes with 2*b2 + b1 == 3 hold the pad.
+__device__ __forceinline__ float warp_reduce12(const float (&v)[12], int lane) {
+    float a[6], b[3];
     const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float send = h4 ? v[i] : v[i + 8];
-        const float keep = h4 ? v[i + 8] : v[i];
+    for (int i = 0; i < 6; ++i) {
+        const float send = h4 ? v[i] : v[i + 6];
+        const float keep = h4 ? v[i + 6] : v[i];
         a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = h3 ? a[i] : a[i + 4];
-        const float keep = h3 ? a[i + 4] : a[i];
+    for (int i = 0; i < 3; ++i) {
+        const float send = h3 ? a[i] : a[i + 3];
+        const float keep = h3 ? a[i + 3] : a[i];
         b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
     }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = h2 ? b[i] : b[i + 2];
-        const float keep = h2 ? b[i + 2] : b[i];
-        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    const float send = h1 ? c[0] : c[1];
-    const float keep = h1 ? c[1] : c[0];
-    float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    const float c0 = (h2 ? b[2] : b[0]) + __shfl_xor_sync(0xffffffffu, h2 ? b[0] : b[2], 4);
+    const float c1 = (h2 ? 0.f : b[1]) + __shfl_xor_sync(0xffffffffu, h2 ? b[1] : 0.f, 4);
+    float r = (h1 ? c1 : c0) + __shfl_xor_sync(0xffffffffu, h1 ? c0 : c1, 2);
     r += __shfl_xor_sync(0xffffffffu, r, 1);
     return r;
 }
@@ -109,6 +103,9 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     for (int i = 0; i < (SB > 0 ? SB : 1); ++i) { acc_sem[i] = 0.f; last_sem[i] = 0.f; }
 
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    // record component this lane owns after warp_reduce12 (11 = nothing)
+    const int red_sub = ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const int red_slot = red_sub < 3 ? ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + red_sub : 11;
 
     // nothing behind the deepest last-contributor of the tile can receive gradient
     int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
@@ -189,7 +186,10 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                     for (int i = 0; i < SB; ++i) sv[i] = i < S ? __ldg(sp + i) : 0.f;
                 }
                 if (active) {
-                    const float inv_1ma = __frcp_rn(1.f - alpha);  // one reciprocal serves T/(1-a) and T_final/(1-a)
+                    // one reciprocal serves T/(1-a) and T_final/(1-a); 1-a lies in [0.01, 1], so the single-instruction
+                    // approximation (1 ulp) needs no range fix-up -- its error is far inside the gradient bar
+                    float inv_1ma;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha));
                     T = T * inv_1ma;
                     const float w_at = alpha * T;
                     float dL_dopa = 0.f;
@@ -230,13 +230,11 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                     g_cw = -0.5f * gdy * dy * dL_dG;
                     g_op = G * dL_dopa;
                 }
-                // warp reduction (16-slot butterfly), then one vector of atomics per (warp, Gaussian):
+                // warp reduction (12-slot butterfly), then one vector of atomics per (warp, Gaussian):
                 // even lanes own one component each of the 48-byte gradient record
-                const float vals[16] = {g_mx, g_my, g_mabs, g_cx, g_cy, g_cw, g_op, g_c0, g_c1, g_c2, g_d,
-                                        0.f, 0.f, 0.f, 0.f, 0.f};
-                const float mine = warp_reduce16(vals, lane);
-                const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                if (!(lane & 1) && slot < 11) atomicAdd(grad_rec + (size_t)gid * GREC + slot, mine);
+                const float vals[12] = {g_mx, g_my, g_mabs, g_cx, g_cy, g_cw, g_op, g_c0, g_c1, g_c2, g_d, 0.f};
+                const float mine = warp_reduce12(vals, lane);
+                if (!(lane & 1) && red_slot < 11) atomicAdd(grad_rec + (size_t)gid * GREC + red_slot, mine);
                 if (SB > 0) {
 #pragma unroll
                     for (int i = 0; i < SB; ++i) {
