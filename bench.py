@@ -162,7 +162,7 @@ def time_region(fn, steps, dist_on):
     return ms
 
 
-def cpu_baseline_sample(sc_cpu, n_tiles=24):
+def cpu_baseline_sample(sc_cpu, n_tiles=96):
     """Pure-PyTorch per-pixel CPU alpha-blend (oracle/torch_blend.py) of a bounded tile sample of the same
     scene, forward + autograd backward, extrapolated to the full tile grid.  Reported, not optimised."""
     from oracle import oracle, torch_blend
