@@ -64,7 +64,15 @@ class BackwardArgs(C.Structure):
     ]
 
 
-# every symbol include/grpg_b200.h declares, with its ctypes signature
+class L1SsimArgs(C.Structure):  # grpg_l1_ssim_args (include/grpg_loss.h)
+    _fields_ = [
+        ("planes", C.c_int), ("planes_per_mask", C.c_int), ("height", C.c_int), ("width", C.c_int),
+        ("img1", _fp), ("img2", _fp), ("mask", _fp), ("coef_l1", C.c_float), ("coef_ssim", C.c_float),
+        ("sums", _fp), ("grad", _fp), ("stream", _fp),
+    ]
+
+
+# every symbol include/grpg_b200.h and include/grpg_loss.h declare, with its ctypes signature
 SYMBOLS = {
     "grpg_get_geometry_layout": (C.c_int, [C.c_int, C.POINTER(GeomLayout)]),
     "grpg_get_binning_layout": (C.c_int, [C.c_longlong, C.POINTER(BinningLayout)]),
@@ -83,6 +91,7 @@ SYMBOLS = {
     "grpg_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
     "grpg_last_error": (C.c_char_p, []),
     "grpg_version": (C.c_int, []),
+    "grpg_l1_ssim": (C.c_int, [C.POINTER(L1SsimArgs)]),
 }
 
 _lib = None

@@ -90,6 +90,8 @@ static unsigned long long* pinned_word() {
     return p;
 }
 
+extern "C" int grpg_loss_fail(const char* msg) { return fail(msg ? msg : "error"); }  // used by loss_ssim.cu
+
 extern "C" {
 
 const char* grpg_last_error(void) { return g_last_error.c_str(); }

@@ -16,9 +16,11 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 def _declared_functions():
-    text = (ROOT / "include" / "grpg_b200.h").read_text()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"\b(grpg_[a-z0-9_]+)\s*\(", text)
+    names = []
+    for header in ("grpg_b200.h", "grpg_loss.h"):
+        text = (ROOT / "include" / header).read_text()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names += re.findall(r"\b(grpg_[a-z0-9_]+)\s*\(", text)
     return sorted(set(names))
 
 
@@ -27,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     declared = _declared_functions()
     assert declared, "header parse failed"
     for name in declared:
-        assert hasattr(lib, name), f"{name} declared in include/grpg_b200.h but not exported"
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
     assert set(declared) == set(_lib.SYMBOLS), "ctypes table and header disagree"
     assert lib.grpg_version() >= 100
 
@@ -90,8 +92,9 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     import subprocess
     structs = {"grpg_forward_args": _lib.ForwardArgs, "grpg_backward_args": _lib.BackwardArgs,
                "grpg_geom_layout": _lib.GeomLayout, "grpg_binning_layout": _lib.BinningLayout,
-               "grpg_image_layout": _lib.ImageLayout}
-    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grpg_b200.h"', 'int main(void){']
+               "grpg_image_layout": _lib.ImageLayout, "grpg_l1_ssim_args": _lib.L1SsimArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grpg_b200.h"', '#include "grpg_loss.h"',
+             'int main(void){']
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} sizeof %zu\\n", sizeof({cname}));')
         for fname, _ in ct._fields_:
