@@ -63,103 +63,180 @@ __global__ void __launch_bounds__(LOSS_THREADS) l1_ssim_kernel(
 #pragma unroll
     for (int k = 0; k < 11; ++k) w[k] = c_win[k];
 
-    // A: stage inputs
-    for (int i = tid; i < LIN * LIN; i += LOSS_THREADS) {
+    // A: stage inputs.  All of a thread's global loads are issued before the first shared store, so the
+    // ~11 x 2 loads per thread are in flight together (the SM holds only two of these CTAs).
+    constexpr int A_ITERS = (LIN * LIN + LOSS_THREADS - 1) / LOSS_THREADS;
+    float va[A_ITERS], vb[A_ITERS];
+#pragma unroll
+    for (int it = 0; it < A_ITERS; ++it) {
+        const int i = tid + it * LOSS_THREADS;
         const int r = i / LIN, c = i - r * LIN;
         const int gy = y0 - 2 * LR + r, gx = x0 - 2 * LR + c;
-        float a = 0.f, b = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        va[it] = 0.f; vb[it] = 0.f;
+        if (i < LIN * LIN && gy >= 0 && gy < H && gx >= 0 && gx < W) {
             const size_t o = (size_t)gy * W + gx;
-            if (!pm || pm[o]) { a = __ldg(p1 + o); b = __ldg(p2 + o); }
+            if (!pm || pm[o]) { va[it] = __ldg(p1 + o); vb[it] = __ldg(p2 + o); }
         }
-        s.x[r][c] = a; s.y[r][c] = b;
     }
-    __syncthreads();
-
-    // B: horizontal pass of the five statistics
-    for (int i = tid; i < LIN * LST; i += LOSS_THREADS) {
-        const int r = i / LST, c = i - r * LST;
-        float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float a = s.x[r][c + k], b = s.y[r][c + k];
-            const float wa = w[k] * a, wb = w[k] * b;
-            sx += wa; sy += wb; sxx = fmaf(wa, a, sxx); syy = fmaf(wb, b, syy); sxy = fmaf(wa, b, sxy);
-        }
-        s.h[0][r][c] = sx; s.h[1][r][c] = sy; s.h[2][r][c] = sxx; s.h[3][r][c] = syy; s.h[4][r][c] = sxy;
+    for (int it = 0; it < A_ITERS; ++it) {
+        const int i = tid + it * LOSS_THREADS;
+        if (i < LIN * LIN) { (&s.x[0][0])[i] = va[it]; (&s.y[0][0])[i] = vb[it]; }
     }
     __syncthreads();
 
-    // C: vertical pass, SSIM value and partials
+    // B: horizontal pass of the five statistics.  One work item = 7 adjacent outputs of one row: 17 staged
+    // pixels are read once (instead of 7 x 11) and their squares/products are formed once per pixel.
+    constexpr int BS = 7, B_STRIPS = LST / BS;  // 42 = 6 x 7
+    for (int item = tid; item < LIN * B_STRIPS; item += LOSS_THREADS) {
+        const int r = item / B_STRIPS, c0 = (item - r * B_STRIPS) * BS;
+        float sx[BS], sy[BS], sxx[BS], syy[BS], sxy[BS];
+#pragma unroll
+        for (int o = 0; o < BS; ++o) { sx[o] = 0.f; sy[o] = 0.f; sxx[o] = 0.f; syy[o] = 0.f; sxy[o] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < BS + 10; ++j) {
+            const float a = s.x[r][c0 + j], b = s.y[r][c0 + j];
+            const float aa = a * a, bb = b * b, ab = a * b;
+#pragma unroll
+            for (int o = 0; o < BS; ++o) {
+                const int k = j - o;
+                if (k >= 0 && k < 11) {
+                    sx[o] = fmaf(w[k], a, sx[o]); sy[o] = fmaf(w[k], b, sy[o]);
+                    sxx[o] = fmaf(w[k], aa, sxx[o]); syy[o] = fmaf(w[k], bb, syy[o]); sxy[o] = fmaf(w[k], ab, sxy[o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < BS; ++o) {
+            s.h[0][r][c0 + o] = sx[o]; s.h[1][r][c0 + o] = sy[o]; s.h[2][r][c0 + o] = sxx[o];
+            s.h[3][r][c0 + o] = syy[o]; s.h[4][r][c0 + o] = sxy[o];
+        }
+    }
+    __syncthreads();
+
+    // C: vertical pass, SSIM value and partials.  One work item = 7 vertically adjacent outputs of one column
+    // (lanes walk along the row: conflict-free): 17 x 5 loads feed 7 x 5 x 11 FMAs.
     const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
     float ssim_acc = 0.f;
-    for (int i = tid; i < LST * LST; i += LOSS_THREADS) {
-        const int r = i / LST, c = i - r * LST;
-        const int gy = y0 - LR + r, gx = x0 - LR + c;
-        float d_mu1 = 0.f, d_e11 = 0.f, d_e12 = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    constexpr int CS = 7, C_STRIPS = LST / CS;
+    for (int item = tid; item < LST * C_STRIPS; item += LOSS_THREADS) {
+        const int strip = item / LST, c = item - strip * LST, r0 = strip * CS;
+        float acc[5][CS];
 #pragma unroll
-            for (int k = 0; k < 11; ++k) {
-                mu1 = fmaf(w[k], s.h[0][r + k][c], mu1); mu2 = fmaf(w[k], s.h[1][r + k][c], mu2);
-                e11 = fmaf(w[k], s.h[2][r + k][c], e11); e22 = fmaf(w[k], s.h[3][r + k][c], e22);
-                e12 = fmaf(w[k], s.h[4][r + k][c], e12);
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int o = 0; o < CS; ++o) acc[q][o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < CS + 10; ++j) {
+            float v[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) v[q] = s.h[q][r0 + j][c];
+#pragma unroll
+            for (int o = 0; o < CS; ++o) {
+                const int k = j - o;
+                if (k >= 0 && k < 11) {
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) acc[q][o] = fmaf(w[k], v[q], acc[q][o]);
+                }
             }
-            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-            const float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
-            const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2;
-            const float B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
-            const float inv = 1.f / (B1 * B2);
-            const float S = (A1 * A2) * inv;  // loss_utils.py:119
-            d_mu1 = 2.f * mu2 * (A2 - A1) * inv - S * (2.f * mu1 / B1 - 2.f * mu1 / B2);
-            d_e11 = -S / B2;
-            d_e12 = 2.f * A1 * inv;
-            // this CTA's own pixels contribute to the sum once
-            if (r >= LR && r < LR + LT && c >= LR && c < LR + LT) ssim_acc += S;
         }
-        s.d[0][r][c] = d_mu1; s.d[1][r][c] = d_e11; s.d[2][r][c] = d_e12;
+        const int gx = x0 - LR + c;
+#pragma unroll
+        for (int o = 0; o < CS; ++o) {
+            const int r = r0 + o, gy = y0 - LR + r;
+            float d_mu1 = 0.f, d_e11 = 0.f, d_e12 = 0.f;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                const float mu1 = acc[0][o], mu2 = acc[1][o], e11 = acc[2][o], e22 = acc[3][o], e12 = acc[4][o];
+                const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+                const float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
+                const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2;
+                const float B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
+                const float iB1 = 1.f / B1, iB2 = 1.f / B2;
+                const float inv = iB1 * iB2;
+                const float S = (A1 * A2) * inv;  // loss_utils.py:119
+                d_mu1 = 2.f * mu2 * (A2 - A1) * inv - S * (2.f * mu1) * (iB1 - iB2);
+                d_e11 = -S * iB2;
+                d_e12 = 2.f * A1 * inv;
+                // this CTA's own pixels contribute to the sum once
+                if (r >= LR && r < LR + LT && c >= LR && c < LR + LT) ssim_acc += S;
+            }
+            s.d[0][r][c] = d_mu1; s.d[1][r][c] = d_e11; s.d[2][r][c] = d_e12;
+        }
     }
     __syncthreads();
 
     if (grad != nullptr) {
-        // D: horizontal pass of the partials (aliases h)
-        for (int i = tid; i < LST * LT; i += LOSS_THREADS) {
-            const int r = i / LT, c = i - r * LT;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        // D: horizontal pass of the partials (aliases h); one work item = 8 adjacent outputs of one row
+        constexpr int DS = 8, D_STRIPS = LT / DS;
+        for (int item = tid; item < LST * D_STRIPS; item += LOSS_THREADS) {
+            const int r = item / D_STRIPS, c0 = (item - r * D_STRIPS) * DS;
+            float acc[3][DS];
 #pragma unroll
-            for (int k = 0; k < 11; ++k) {
-                a0 = fmaf(w[k], s.d[0][r][c + k], a0); a1 = fmaf(w[k], s.d[1][r][c + k], a1);
-                a2 = fmaf(w[k], s.d[2][r][c + k], a2);
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int o = 0; o < DS; ++o) acc[q][o] = 0.f;
+#pragma unroll
+            for (int j = 0; j < DS + 10; ++j) {
+                const float v0 = s.d[0][r][c0 + j], v1 = s.d[1][r][c0 + j], v2 = s.d[2][r][c0 + j];
+#pragma unroll
+                for (int o = 0; o < DS; ++o) {
+                    const int k = j - o;
+                    if (k >= 0 && k < 11) {
+                        acc[0][o] = fmaf(w[k], v0, acc[0][o]); acc[1][o] = fmaf(w[k], v1, acc[1][o]);
+                        acc[2][o] = fmaf(w[k], v2, acc[2][o]);
+                    }
+                }
             }
-            s.hd[0][r][c] = a0; s.hd[1][r][c] = a1; s.hd[2][r][c] = a2;
+#pragma unroll
+            for (int o = 0; o < DS; ++o) {
+                s.hd[0][r][c0 + o] = acc[0][o]; s.hd[1][r][c0 + o] = acc[1][o]; s.hd[2][r][c0 + o] = acc[2][o];
+            }
         }
         __syncthreads();
     }
 
-    // E: vertical pass, gradient, L1
+    // E: vertical pass, gradient, L1; one work item = 4 vertically adjacent pixels of one column (256 items)
     float l1_acc = 0.f;
-    for (int i = tid; i < LT * LT; i += LOSS_THREADS) {
-        const int r = i / LT, c = i - r * LT;
-        const int gy = y0 + r, gx = x0 + c;
-        if (gy >= H || gx >= W) continue;
-        const size_t o = (size_t)gy * W + gx;
-        const bool valid = !pm || pm[o];
-        const float a = s.x[r + 2 * LR][c + 2 * LR], b = s.y[r + 2 * LR][c + 2 * LR];  // already 0 when masked
-        const float diff = a - b;
-        if (valid) l1_acc += fabsf(diff);
-        if (grad != nullptr) {
-            float g = 0.f;
-            if (valid) {
-                float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    constexpr int ES = 4;
+    {
+        const int c = tid & (LT - 1), r0 = (tid / LT) * ES;
+        const int gx = x0 + c;
+        float acc[3][ES];
 #pragma unroll
-                for (int k = 0; k < 11; ++k) {
-                    g0 = fmaf(w[k], s.hd[0][r + k][c], g0); g1 = fmaf(w[k], s.hd[1][r + k][c], g1);
-                    g2 = fmaf(w[k], s.hd[2][r + k][c], g2);
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int o = 0; o < ES; ++o) acc[q][o] = 0.f;
+        if (grad != nullptr) {
+#pragma unroll
+            for (int j = 0; j < ES + 10; ++j) {
+                const float v0 = s.hd[0][r0 + j][c], v1 = s.hd[1][r0 + j][c], v2 = s.hd[2][r0 + j][c];
+#pragma unroll
+                for (int o = 0; o < ES; ++o) {
+                    const int k = j - o;
+                    if (k >= 0 && k < 11) {
+                        acc[0][o] = fmaf(w[k], v0, acc[0][o]); acc[1][o] = fmaf(w[k], v1, acc[1][o]);
+                        acc[2][o] = fmaf(w[k], v2, acc[2][o]);
+                    }
                 }
-                const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);  // torch.abs backward: sign(0) = 0
-                g = coef_l1 * sgn + coef_ssim * (g0 + 2.f * a * g1 + b * g2);
             }
-            grad[plane * hw + o] = g;
+        }
+#pragma unroll
+        for (int o = 0; o < ES; ++o) {
+            const int r = r0 + o, gy = y0 + r;
+            if (gy >= H || gx >= W) continue;
+            const size_t off = (size_t)gy * W + gx;
+            const bool valid = !pm || pm[off];
+            const float a = s.x[r + 2 * LR][c + 2 * LR], b = s.y[r + 2 * LR][c + 2 * LR];  // already 0 when masked
+            const float diff = a - b;
+            if (valid) l1_acc += fabsf(diff);
+            if (grad != nullptr) {
+                float g = 0.f;
+                if (valid) {
+                    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);  // torch.abs backward: sign(0) = 0
+                    g = coef_l1 * sgn + coef_ssim * (acc[0][o] + 2.f * a * acc[1][o] + b * acc[2][o]);
+                }
+                grad[plane * hw + off] = g;
+            }
         }
     }
 
