@@ -281,10 +281,30 @@ def main():
         img_host.copy_(out[0], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    # what the simulator node consumes: the clamped frame as interleaved uint8 on the host (simulator.py:313-314).
+    # Reference arm: its literal expressions (float D2H, numpy transpose/scale/cast).  Ours: the fused epilogue
+    # kernel storing the bytes straight into pinned memory (gaussianrpg_b200/image_utils.py).
+    if args.impl == "ours":
+        from gaussianrpg_b200 import image_utils
+
+        def e2e_rgb8():
+            cam = cam_host.to(dev, non_blocking=True)
+            out = fwd_only(cam[:16].view(4, 4), cam[16:32].view(4, 4), cam[32:35])
+            return image_utils.to_host_rgb8(out[0])
+    else:
+        import numpy as _np
+
+        def e2e_rgb8():
+            cam = cam_host.to(dev, non_blocking=True)
+            out = fwd_only(cam[:16].view(4, 4), cam[16:32].view(4, 4), cam[32:35])
+            rgb = torch.clamp(out[0], 0., 1.)
+            return (rgb.detach().cpu().numpy().transpose(1, 2, 0) * 255).astype(_np.uint8)
+
     for _ in range(3):
-        e2e_fb(); e2e_f()
+        e2e_fb(); e2e_f(); e2e_rgb8()
     ms_e2e_fb = time_region(e2e_fb, args.steps, False)
     ms_e2e_f = time_region(e2e_f, args.steps, False)
+    ms_e2e_rgb8 = time_region(e2e_rgb8, args.steps, False)
     clk = clocks.stop()
 
     # scene statistics (one extra forward)
@@ -314,6 +334,10 @@ def main():
                      "joined before the loss), loss scalar D2H; Gaussian parameters are model state resident in HBM"},
         e2e_fwd={"value": 1000.0 * args.steps / ms_e2e_f, "unit": "frames/s", "h2d_bytes_per_step": int(cam_host.numel() * 4),
                  "d2h_bytes_per_step": int(img_host.numel() * 4)},
+        e2e_fwd_rgb8={"value": 1000.0 * args.steps / ms_e2e_rgb8, "unit": "frames/s",
+                      "h2d_bytes_per_step": int(cam_host.numel() * 4),
+                      "d2h_bytes_per_step": int(H * W * 3 if args.impl == "ours" else img_host.numel() * 4),
+                      "note": "clamped frame delivered to the host as uint8 HWC (what simulator.py:313-314 produces)"},
         clocks={"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         config={"workload": workload, "P": P, "V": V, "R": R,
                 "R_binned": base.get("index_check", {}).get("binned", R), "width": W, "height": H,

@@ -72,7 +72,14 @@ class L1SsimArgs(C.Structure):  # grpg_l1_ssim_args (include/grpg_loss.h)
     ]
 
 
-# every symbol include/grpg_b200.h and include/grpg_loss.h declare, with its ctypes signature
+class Rgb8Args(C.Structure):  # grpg_rgb8_args (include/grpg_image.h)
+    _fields_ = [
+        ("height", C.c_int), ("width", C.c_int), ("rgb", _fp), ("acc", _fp), ("sky", _fp), ("out_rgb8", _fp),
+        ("out_rgb", _fp), ("stream", _fp),
+    ]
+
+
+# every symbol include/*.h declare, with its ctypes signature
 SYMBOLS = {
     "grpg_get_geometry_layout": (C.c_int, [C.c_int, C.POINTER(GeomLayout)]),
     "grpg_get_binning_layout": (C.c_int, [C.c_longlong, C.POINTER(BinningLayout)]),
@@ -92,6 +99,7 @@ SYMBOLS = {
     "grpg_last_error": (C.c_char_p, []),
     "grpg_version": (C.c_int, []),
     "grpg_l1_ssim": (C.c_int, [C.POINTER(L1SsimArgs)]),
+    "grpg_compose_rgb8": (C.c_int, [C.POINTER(Rgb8Args)]),
 }
 
 _lib = None
