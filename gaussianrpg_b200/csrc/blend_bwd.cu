@@ -11,11 +11,13 @@
 // atomics per (warp, Gaussian) -- lanes 0..10 each add one component of the 48-byte gradient
 // record, so the 11 adds leave the SM as a single coalesced RED request.
 #include "grpg_common.cuh"
+#include <stdlib.h>
 
 namespace grpg {
 
 constexpr int BWD_BATCH = 256;
 constexpr int GREC = 12;  // floats per Gaussian in the gradient record
+#define GRPG_BWD_PPL_DEFAULT 2  // measured on the 2 M scene: 1 -> 1.21 ms, 2 -> 1.08 ms, 4 -> 1.20 ms
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -250,6 +252,219 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     cp_async_wait_all();  // nothing may be in flight into shared memory when the CTA retires
 }
 
+
+// ---- wide variant (no semantic channels): PPL pixels per lane ------------------------------------------------------
+// A warp owns an 8 x (4*PPL) pixel block and lane l the pixels (l&7, (l>>3) + 4p), p < PPL.  The 12-slot butterfly
+// and the RED vector -- 50 of the ~185 warp instructions of a (warp, Gaussian) pair in the one-pixel layout -- and
+// the queue/record loads are then paid once per 32*PPL pixels; each lane adds its PPL partials in registers first.
+// Per-pixel arithmetic is the same sequence as in blend_bwd_kernel.
+template <int PPL, int MINB>
+__global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const Rec* __restrict__ rec, int W, int H,
+    const float* __restrict__ bg_color, const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
+    const float* __restrict__ dL_dalphas, float* __restrict__ grad_rec /*[P][12]*/, int HL, int row_stride,
+    int row_phase) {
+    constexpr int NT = 256 / PPL, NW = 8 / PPL, RPT = BWD_BATCH / NT;
+    __shared__ __align__(16) float4 s_rec2[2][BWD_BATCH * 3];
+    __shared__ uint32_t s_id2[2][BWD_BATCH];
+    __shared__ int s_maxlast[NW];
+    __shared__ uint16_t s_q[NW][BWD_BATCH];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
+    const uint32_t tile = blockIdx.y * tiles_x + blockIdx.x;
+    const int bx0 = blockIdx.x * GRPG_TILE + (warp & 1) * 8;
+    const int wy0 = (warp >> 1) * 4 * PPL;
+    const int by0 = (blockIdx.y * row_stride + row_phase) * GRPG_TILE + wy0;
+    const int pix_x = bx0 + (lane & 7);
+    const float pxf = (float)pix_x;
+    const float bx_lo = (float)bx0, bx_hi = (float)(bx0 + 7), by_lo = (float)by0, by_hi = (float)(by0 + 4 * PPL - 1);
+    const size_t hw = (size_t)HL * W;
+
+    const uint2 range = ranges[tile];
+    const int n_inst = (int)(range.y - range.x);
+    const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
+
+    float pyf[PPL], T[PPL], T_final[PPL], dpix0[PPL], dpix1[PPL], dpix2[PPL], dpix_depth[PPL], dpix_alpha[PPL], bgdot[PPL];
+    float acc0[PPL], acc1[PPL], acc2[PPL], acc_depth[PPL], acc_alpha[PPL];
+    float lastc0[PPL], lastc1[PPL], lastc2[PPL], last_depth[PPL], last_alpha[PPL];
+    int last_contributor[PPL];
+    int lmax = 0;
+#pragma unroll
+    for (int p = 0; p < PPL; ++p) {
+        const int pix_y = by0 + (lane >> 3) + 4 * p;
+        const int loc_y = blockIdx.y * GRPG_TILE + wy0 + (lane >> 3) + 4 * p;
+        const bool inside = pix_x < W && pix_y < H;
+        const size_t pid = (size_t)loc_y * W + pix_x;
+        pyf[p] = (float)pix_y;
+        T_final[p] = inside ? 1.0f - alphas[pid] : 0.0f;
+        T[p] = T_final[p];
+        last_contributor[p] = inside ? (int)n_contrib[pid] : 0;
+        lmax = max(lmax, last_contributor[p]);
+        dpix0[p] = inside ? dL_dpixels[pid] : 0.f;
+        dpix1[p] = inside ? dL_dpixels[hw + pid] : 0.f;
+        dpix2[p] = inside ? dL_dpixels[2 * hw + pid] : 0.f;
+        dpix_depth[p] = inside ? dL_dpixel_depths[pid] : 0.f;
+        dpix_alpha[p] = inside ? dL_dalphas[pid] : 0.f;
+        bgdot[p] = bg0 * dpix0[p] + bg1 * dpix1[p] + bg2 * dpix2[p];
+        acc0[p] = acc1[p] = acc2[p] = acc_depth[p] = acc_alpha[p] = 0.f;
+        lastc0[p] = lastc1[p] = lastc2[p] = last_depth[p] = last_alpha[p] = 0.f;
+    }
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    const int red_sub = ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const int red_slot = red_sub < 3 ? ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + red_sub : 11;
+
+    const int wmax = __reduce_max_sync(0xffffffffu, lmax);
+    if (lane == 0) s_maxlast[warp] = wmax;
+    __syncthreads();
+    int tile_last = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) tile_last = max(tile_last, s_maxlast[w]);
+    tile_last = min(tile_last, n_inst);
+
+    auto stage = [&](int buf, int top, const uint32_t (&id)[RPT]) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int t = tid + r * NT;
+            if (top - 1 - t >= 0) {
+                const float4* src = reinterpret_cast<const float4*>(rec + id[r]);
+                float4* d = &s_rec2[buf][3 * t];
+                cp_async16(d, src); cp_async16(d + 1, src + 1); cp_async16(d + 2, src + 2);
+                s_id2[buf][t] = id[r];
+            }
+        }
+        cp_async_commit();
+    };
+    auto fetch_id = [&](int top, uint32_t (&id)[RPT]) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int t = tid + r * NT;
+            id[r] = top - 1 - t >= 0 ? point_list[range.x + top - 1 - t] : 0u;
+        }
+    };
+    uint32_t id_next[RPT];
+    fetch_id(tile_last, id_next);
+    stage(0, tile_last, id_next);
+    fetch_id(tile_last - BWD_BATCH, id_next);
+
+    for (int top = tile_last, it = 0; top > 0; top -= BWD_BATCH, ++it) {
+        const int cnt = min(BWD_BATCH, top);
+        cp_async_wait_all();
+        __syncthreads();
+        const float4* s_rec = s_rec2[it & 1];
+        const uint32_t* s_id = s_id2[it & 1];
+        stage((it + 1) & 1, top - BWD_BATCH, id_next);
+        fetch_id(top - 2 * BWD_BATCH, id_next);
+        if (wmax <= top - cnt) continue;
+
+        uint16_t* q = s_q[warp];
+        const char* rec_base = reinterpret_cast<const char*>(s_rec);
+        int n_q = 0;
+        for (int g0 = 0; g0 < cnt; g0 += 32) {
+            const int j = g0 + lane;
+            const bool hit = j < cnt && (top - 1 - j) < wmax &&
+                             footprint_hits_exact(s_rec[3 * j], s_rec[3 * j + 1], bx_lo, bx_hi, by_lo, by_hi);
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+            n_q += __popc(m);
+        }
+        __syncwarp();
+        for (int qi = 0; qi < n_q; ++qi) {
+            const int k = (int)q[qi];
+            const float4* rk = reinterpret_cast<const float4*>(rec_base + (uint32_t)k * 48u);
+            const int pos = top - 1 - k;
+            const float4 a = rk[0];
+            const float4 b = rk[1];
+            const uint32_t gid = s_id[k];
+            const float dx = a.x - pxf;
+            const float dxA = fmul(dx, b.x), dxB = fmul(dx, b.y);
+            float dy[PPL], power[PPL];
+            bool maybe[PPL], any_maybe = false;
+#pragma unroll
+            for (int p = 0; p < PPL; ++p) {
+                dy[p] = a.y - pyf[p];
+                power[p] = ffma(ffma(dx, dxA, fmul(dy[p], fmul(dy[p], b.z))), -0.5f, -fmul(dy[p], dxB));
+                maybe[p] = (pos < last_contributor[p]) && !(power[p] > 0.0f) && !(power[p] < a.w);
+                any_maybe |= maybe[p];
+            }
+            if (!__any_sync(0xffffffffu, any_maybe)) continue;
+            float G[PPL], alpha[PPL];
+            bool active[PPL], any_active = false;
+#pragma unroll
+            for (int p = 0; p < PPL; ++p) {
+                G[p] = expf(power[p]);
+                alpha[p] = fminf(0.99f, b.w * G[p]);
+                active[p] = maybe[p] && (alpha[p] >= 1.0f / 255.0f);
+                any_active |= active[p];
+            }
+            if (!__any_sync(0xffffffffu, any_active)) continue;
+
+            const float4 c = rk[2];
+            float vals[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) vals[i] = 0.f;
+#pragma unroll
+            for (int p = 0; p < PPL; ++p) {
+                if (active[p]) {
+                    float inv_1ma;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha[p]));
+                    T[p] = T[p] * inv_1ma;
+                    const float w_at = alpha[p] * T[p];
+                    const float la = last_alpha[p], one_m_la = 1.f - la;
+                    float dL_dopa = 0.f;
+                    acc0[p] = la * lastc0[p] + one_m_la * acc0[p]; lastc0[p] = c.x;
+                    dL_dopa += (c.x - acc0[p]) * dpix0[p];
+                    acc1[p] = la * lastc1[p] + one_m_la * acc1[p]; lastc1[p] = c.y;
+                    dL_dopa += (c.y - acc1[p]) * dpix1[p];
+                    acc2[p] = la * lastc2[p] + one_m_la * acc2[p]; lastc2[p] = c.z;
+                    dL_dopa += (c.z - acc2[p]) * dpix2[p];
+                    acc_depth[p] = la * last_depth[p] + one_m_la * acc_depth[p]; last_depth[p] = c.w;
+                    dL_dopa += (c.w - acc_depth[p]) * dpix_depth[p];
+                    acc_alpha[p] = la + one_m_la * acc_alpha[p];
+                    dL_dopa += (1.f - acc_alpha[p]) * dpix_alpha[p];
+                    dL_dopa *= T[p];
+                    last_alpha[p] = alpha[p];
+                    dL_dopa += (-T_final[p] * inv_1ma) * bgdot[p];
+
+                    const float dL_dG = b.w * dL_dopa;
+                    const float gdx = G[p] * dx, gdy = G[p] * dy[p];
+                    const float dG_ddelx = -gdx * b.x - gdy * b.y;
+                    const float dG_ddely = -gdy * b.z - gdx * b.y;
+                    const float g_mx = dL_dG * dG_ddelx * ddelx_dx;
+                    const float g_my = dL_dG * dG_ddely * ddely_dy;
+                    vals[0] += g_mx;
+                    vals[1] += g_my;
+                    vals[2] += fabsf(g_mx) + fabsf(g_my);
+                    const float hG = -0.5f * dL_dG;
+                    vals[3] += hG * gdx * dx;
+                    vals[4] += hG * gdx * dy[p];
+                    vals[5] += hG * gdy * dy[p];
+                    vals[6] += G[p] * dL_dopa;
+                    vals[7] += w_at * dpix0[p];
+                    vals[8] += w_at * dpix1[p];
+                    vals[9] += w_at * dpix2[p];
+                    vals[10] += w_at * dpix_depth[p];
+                }
+            }
+            const float mine = warp_reduce12(vals, lane);
+            if (!(lane & 1) && red_slot < 11) atomicAdd(grad_rec + (size_t)gid * GREC + red_slot, mine);
+        }
+    }
+    cp_async_wait_all();
+}
+
+// pixels per lane of the S == 0 backward blend (1 = blend_bwd_kernel<0>); GRPG_BWD_PPL overrides for A/B runs
+static int bwd_pixels_per_lane() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GRPG_BWD_PPL");
+        v = e ? atoi(e) : GRPG_BWD_PPL_DEFAULT;
+        if (v != 1 && v != 2) v = GRPG_BWD_PPL_DEFAULT;
+    }
+    return v;
+}
+
 void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const uint32_t* point_list, const Rec* rec,
                       const uint32_t* n_contrib, float* grad_rec, cudaStream_t stream) {
     const int stride = a->tile_row_stride > 1 ? a->tile_row_stride : 1, phase = a->tile_row_stride > 1 ? a->tile_row_phase : 0;
@@ -262,12 +477,19 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
     blend_bwd_kernel<SBV><<<grid, 256, 0, stream>>>(ranges, point_list, rec, a->semantics, S, a->width, a->height,  \
                                                      a->background, a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth, \
                                                      a->dL_dalphas, a->dL_dpix_semantic, grad_rec, a->dL_dsemantic, HL, stride, phase)
-    if (S == 0) GRPG_BWD_LAUNCH(0);
+    const int ppl = S == 0 ? bwd_pixels_per_lane() : 1;
+#define GRPG_BWD_WIDE(PPLV, MINBV)                                                                                         \
+    blend_bwd_wide_kernel<PPLV, MINBV><<<grid, 256 / PPLV, 0, stream>>>(ranges, point_list, rec, a->width, a->height,      \
+                                                                 a->background, a->alphas, n_contrib, a->dL_dpix,    \
+                                                                 a->dL_dpix_depth, a->dL_dalphas, grad_rec, HL, stride, phase)
+    if (ppl == 2) GRPG_BWD_WIDE(2, 5);  // 95 registers, 5 CTAs of 4 warps per SM: the measured optimum (4: 1.17 ms, 5: 1.08, 6-7: 1.09, 8: 1.28)
+    else if (S == 0) GRPG_BWD_LAUNCH(0);
     else if (S <= 4) GRPG_BWD_LAUNCH(4);
     else if (S <= 8) GRPG_BWD_LAUNCH(8);
     else if (S <= 16) GRPG_BWD_LAUNCH(16);
     else GRPG_BWD_LAUNCH(32);
 #undef GRPG_BWD_LAUNCH
+#undef GRPG_BWD_WIDE
 }
 
 }  // namespace grpg
