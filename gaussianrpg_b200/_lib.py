@@ -79,6 +79,20 @@ class Rgb8Args(C.Structure):  # grpg_rgb8_args (include/grpg_image.h)
     ]
 
 
+COMPOSE_MAX_FOURIER = 16
+
+
+class ComposeSubmodel(C.Structure):  # grpg_compose_submodel (include/grpg_compose.h)
+    _fields_ = [
+        ("n", C.c_int), ("is_actor", C.c_int), ("fourier_dim", C.c_int), ("reserved", C.c_int),
+        ("xyz", _fp), ("scaling", _fp), ("rotation", _fp), ("opacity", _fp), ("features_dc", _fp),
+        ("features_rest", _fp), ("flip_mask", _fp),
+        ("obj_rot", _fp), ("obj_trans", _fp), ("idft", C.c_float * COMPOSE_MAX_FOURIER),
+        ("d_xyz", _fp), ("d_scaling", _fp), ("d_rotation", _fp), ("d_opacity", _fp), ("d_features_dc", _fp),
+        ("d_features_rest", _fp),
+    ]
+
+
 # every symbol include/*.h declare, with its ctypes signature
 SYMBOLS = {
     "grpg_get_geometry_layout": (C.c_int, [C.c_int, C.POINTER(GeomLayout)]),
@@ -100,6 +114,10 @@ SYMBOLS = {
     "grpg_version": (C.c_int, []),
     "grpg_l1_ssim": (C.c_int, [C.POINTER(L1SsimArgs)]),
     "grpg_compose_rgb8": (C.c_int, [C.POINTER(Rgb8Args)]),
+    "grpg_compose_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "grpg_compose_forward": (C.c_int, [C.POINTER(ComposeSubmodel), C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "grpg_compose_backward": (C.c_int, [C.POINTER(ComposeSubmodel), C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                        _fp, _fp]),
 }
 
 _lib = None

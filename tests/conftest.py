@@ -19,3 +19,9 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    from pathlib import Path
+    return Path(__file__).resolve().parent / "golden"

@@ -17,7 +17,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 def _declared_functions():
     names = []
-    for header in ("grpg_b200.h", "grpg_loss.h", "grpg_image.h"):
+    for header in sorted(p.name for p in (ROOT / "include").glob("*.h")):
         text = (ROOT / "include" / header).read_text()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names += re.findall(r"\b(grpg_[a-z0-9_]+)\s*\(", text)
@@ -92,8 +92,9 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     import subprocess
     structs = {"grpg_forward_args": _lib.ForwardArgs, "grpg_backward_args": _lib.BackwardArgs,
                "grpg_geom_layout": _lib.GeomLayout, "grpg_binning_layout": _lib.BinningLayout,
-               "grpg_image_layout": _lib.ImageLayout, "grpg_l1_ssim_args": _lib.L1SsimArgs, "grpg_rgb8_args": _lib.Rgb8Args}
-    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grpg_b200.h"', '#include "grpg_loss.h"', '#include "grpg_image.h"',
+               "grpg_image_layout": _lib.ImageLayout, "grpg_l1_ssim_args": _lib.L1SsimArgs, "grpg_rgb8_args": _lib.Rgb8Args,
+               "grpg_compose_submodel": _lib.ComposeSubmodel}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grpg_b200.h"', '#include "grpg_loss.h"', '#include "grpg_image.h"', '#include "grpg_compose.h"',
              'int main(void){']
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} sizeof %zu\\n", sizeof({cname}));')
