@@ -93,6 +93,18 @@ class ComposeSubmodel(C.Structure):  # grpg_compose_submodel (include/grpg_compo
     ]
 
 
+class AdamTensor(C.Structure):  # grpg_adam_tensor (include/grpg_optim.h)
+    _fields_ = [
+        ("param", _fp), ("grad", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("numel", C.c_longlong),
+        ("one_minus_beta1", C.c_float), ("beta2", C.c_float), ("one_minus_beta2", C.c_float), ("step_size", C.c_float),
+        ("bias_correction2_sqrt", C.c_float), ("eps", C.c_float),
+    ]
+
+
+class StatsSubmodel(C.Structure):  # grpg_stats_submodel (include/grpg_optim.h)
+    _fields_ = [("n", C.c_int), ("reserved", C.c_int), ("max_radii2D", _fp), ("xyz_gradient_accum", _fp), ("denom", _fp)]
+
+
 # every symbol include/*.h declare, with its ctypes signature
 SYMBOLS = {
     "grpg_get_geometry_layout": (C.c_int, [C.c_int, C.POINTER(GeomLayout)]),
@@ -114,6 +126,10 @@ SYMBOLS = {
     "grpg_version": (C.c_int, []),
     "grpg_l1_ssim": (C.c_int, [C.POINTER(L1SsimArgs)]),
     "grpg_compose_rgb8": (C.c_int, [C.POINTER(Rgb8Args)]),
+    "grpg_adam_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "grpg_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int, _fp, _fp]),
+    "grpg_stats_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "grpg_densify_stats": (C.c_int, [C.POINTER(StatsSubmodel), C.c_int, _fp, _fp, _fp, _fp]),
     "grpg_compose_workspace_bytes": (C.c_size_t, [C.c_int]),
     "grpg_compose_forward": (C.c_int, [C.POINTER(ComposeSubmodel), C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "grpg_compose_backward": (C.c_int, [C.POINTER(ComposeSubmodel), C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
