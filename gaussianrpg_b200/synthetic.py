@@ -162,6 +162,7 @@ def street_scene(P: int = 2_000_000, W: int = 1920, H: int = 1280, n_actors: int
     scales_bg[torch.arange(n_bg), thin] *= 0.2
     rots_bg = torch.nn.functional.normalize(torch.randn(n_bg, 4, generator=g), dim=1)
     scales, rots = [scales_bg], [rots_bg]
+    graph = []  # per actor: (local xyz, local quaternion, pose quaternion, pose translation) -- see street_scene_graph
     if n_act:
         lanes = [-1.75, 1.75, -5.25, 5.25]
         for a in range(n_actors):
@@ -173,6 +174,7 @@ def street_scene(P: int = 2_000_000, W: int = 1920, H: int = 1280, n_actors: int
             means.append(local @ Rm.t() + trans)
             q_local = torch.nn.functional.normalize(torch.randn(actor_points, 4, generator=g), dim=1)
             rots.append(torch.nn.functional.normalize(_quat_mul(q_obj.expand_as(q_local), q_local), dim=1))
+            graph.append((local, q_local, q_obj, trans))
             scales.append(torch.exp(torch.randn(actor_points, 3, generator=g) * 0.5 + math.log(0.05)))
     means3D = torch.cat(means, 0).float().contiguous()
     P_tot = means3D.shape[0]
@@ -188,4 +190,41 @@ def street_scene(P: int = 2_000_000, W: int = 1920, H: int = 1280, n_actors: int
     return Scene(width=W, height=H, tanfovx=W / (2 * f), tanfovy=H / (2 * f), viewmatrix=view, projmatrix=full,
                  campos=campos, bg=torch.zeros(3), means3D=means3D, opacities=opac,
                  scales=torch.cat(scales, 0).float().contiguous(), rotations=torch.cat(rots, 0).float().contiguous(),
-                 shs=shs.contiguous(), sh_degree=sh_degree, name=f"street_P{P_tot}_{W}x{H}")
+                 shs=shs.contiguous(), sh_degree=sh_degree, name=f"street_P{P_tot}_{W}x{H}",
+                 extra={"n_bkgd": n_bg, "graph": graph})
+
+
+def street_scene_graph(sc: Scene, fourier_dim: int = 5, time: float = 0.3, seed: int = 1):
+    """The sub-model parameters behind `street_scene` in the reference's storage format (gaussian_model.py:207-251:
+    raw xyz, log-scales, raw quaternions, opacity logits, SH dc / rest; actors with `fourier_dim` dc rows,
+    gaussian_model_actor.py:73-82) plus the per-actor pose, such that composing them
+    (street_gaussian_model.py:295-384) reproduces the scene's rasterizer inputs.  Returns
+    (background dict, [actor dicts], obj_rots [K,4], obj_trans [K,3], idft [K][F])."""
+    from .scene_compose import idft_base
+    g = torch.Generator().manual_seed(seed)
+    n_bg, graph = sc.extra["n_bkgd"], sc.extra["graph"]
+
+    def sub(sl, xyz, rot, F):
+        n = xyz.shape[0]
+        dc = torch.zeros(n, F, 3)
+        base = torch.tensor(idft_base(time, F))
+        dc[:, 0] = sc.shs[sl, 0]  # idft[0] = cos(0) = 1: the composed dc equals the scene's when the other rows are 0
+        if F > 1:
+            extra = torch.randn(n, F - 1, 3, generator=g) * 0.05
+            dc[:, 1:] = extra
+            dc[:, 0] -= (extra * base[1:, None]).sum(1)
+        o = sc.opacities[sl].clamp(1e-6, 1 - 1e-6)
+        return dict(xyz=xyz.contiguous(), scaling=torch.log(sc.scales[sl]).contiguous(), rotation=rot.contiguous(),
+                    opacity=torch.log(o / (1 - o)).contiguous(), features_dc=dc.contiguous(),
+                    features_rest=sc.shs[sl, 1:].contiguous())
+
+    bk = sub(slice(0, n_bg), sc.means3D[:n_bg], sc.rotations[:n_bg], 1)
+    actors, off = [], n_bg
+    for local, q_local, _, _ in graph:
+        n = local.shape[0]
+        actors.append(sub(slice(off, off + n), local, q_local, fourier_dim))
+        off += n
+    K = len(graph)
+    obj_rots = torch.stack([q for _, _, q, _ in graph]) if K else torch.zeros(0, 4)
+    obj_trans = torch.stack([t for _, _, _, t in graph]) if K else torch.zeros(0, 3)
+    return bk, actors, obj_rots, obj_trans, [idft_base(time, fourier_dim) for _ in range(K)]
