@@ -17,8 +17,14 @@ from . import _lib
 NUM_CHANNELS = 3
 
 
+_cuda_ok = None
+
+
 def _require_cuda():
-    if not torch.cuda.is_available():
+    global _cuda_ok
+    if _cuda_ok is None:  # torch.cuda.is_available() costs ~10 us per call (NVML probe): ask once
+        _cuda_ok = bool(torch.cuda.is_available())
+    if not _cuda_ok:
         raise RuntimeError("gaussianrpg_b200 needs a CUDA device (sm_100a); there is no CPU path")
 
 
@@ -35,8 +41,11 @@ def _ptr(t) -> int | None:
     return t.data_ptr()
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(dev=None) -> int:
+    """Raw handle of the current PyTorch stream (torch.cuda.current_stream() builds a Stream object through
+    several Python layers, ~25 us; the raw query is sub-microsecond)."""
+    idx = dev.index if dev is not None and dev.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
 
 
 def _check(rc: int):
@@ -130,7 +139,7 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
     a.out_semantic = _ptr(out_semantic)
     a.radii = radii.data_ptr()
     a.geom_ws, a.image_ws, a.binning_ws = geom.data_ptr(), img.data_ptr(), None
-    a.stream = _stream()
+    a.stream = _stream(dev)
     a.tile_row_stride, a.tile_row_phase = stride, phase
     a.forward_only = int(bool(_forward_only))
     a.reference_binning = int(bool(_reference_binning))
@@ -155,7 +164,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                  dL_dout_depth, dL_dout_alpha, dL_dout_semantic, sh, degree, campos, geomBuffer, R,
                                  binningBuffer, imageBuffer, alphas, semantics, debug, *, _band=(1, 0), _height=None,
-                                 _width=None, _stage=3, _grad_rec=None, _slice=None, _peer_grad=None):
+                                 _width=None, _stage=3, _grad_rec=None, _slice=None, _peer_grad=None, _wanted=None):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:126-220).
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
@@ -166,7 +175,9 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     blend backward and returns (grad_rec[P,12], dL_dsemantic[P,S]); `_stage=2` runs only the per-Gaussian
     backward for `_slice=(p_begin, p_count)` from `_grad_rec[p_count,12]` and returns p_count-row gradients;
     with `_peer_grad` (peer-mapped pointers to every rank's full [P,12] record buffer) stage 2 sums the records
-    over the ranks while loading them instead of reading `_grad_rec`.
+    over the ranks while loading them instead of reading `_grad_rec`.  `_wanted=(means2D, colors, cov3D, scale_rot)`
+    (booleans; the autograd function passes `ctx.needs_input_grad`) skips allocating and writing the outputs nobody
+    reads -- they come back as None -- as well as the two internal ones (dL_dconic, dL_ddepth).
     """
     _require_cuda()
     lib = _lib.load()
@@ -195,9 +206,14 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         Pout = 0  # no per-parameter outputs in the blend-only stage
     P_full = P
     P = Pout
-    dL_dmeans3D, dL_dmeans2D, dL_dcolors = out(P, 3), out(P, 3), out(P, NUM_CHANNELS)
-    dL_ddepths, dL_dconic, dL_dopacity = out(P, 1), out(P, 2, 2), out(P, 1)
-    dL_dcov3D, dL_dsh, dL_dscales, dL_drot = out(P, 6), out(P, M, 3), out(P, 3), out(P, 4)
+    w_m2d, w_col, w_cov, w_sr = (True, True, True, True) if _wanted is None else (bool(x) for x in _wanted)
+    internal = _wanted is None  # the raw entry point mirrors the reference and materialises everything
+    dL_dmeans3D, dL_dopacity, dL_dsh = out(P, 3), out(P, 1), out(P, M, 3)
+    dL_dmeans2D = out(P, 3) if w_m2d else None
+    dL_dcolors = out(P, NUM_CHANNELS) if w_col else None
+    dL_ddepths, dL_dconic = (out(P, 1), out(P, 2, 2)) if internal else (None, None)
+    dL_dcov3D = out(P, 6) if w_cov else None
+    dL_dscales, dL_drot = (out(P, 3), out(P, 4)) if w_sr else (None, None)
     dL_dsemantic = out(P_full if _stage != 2 else P, S)
     P = P_full
     if P == 0:
@@ -228,16 +244,16 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     a.geom_ws, a.binning_ws, a.image_ws = _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer)
     a.dL_dpix, a.dL_dpix_depth = _ptr(opt(dL_dout_color)), _ptr(opt(dL_dout_depth))
     a.dL_dalphas, a.dL_dpix_semantic = _ptr(opt(dL_dout_alpha)), _ptr(opt(dL_dout_semantic))
-    a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = dL_dmeans2D.data_ptr(), dL_dconic.data_ptr(), dL_dopacity.data_ptr()
-    a.dL_dcolor, a.dL_ddepth, a.dL_dmean3D = dL_dcolors.data_ptr(), dL_ddepths.data_ptr(), dL_dmeans3D.data_ptr()
-    a.dL_dcov3D, a.dL_dsh = dL_dcov3D.data_ptr(), _ptr(dL_dsh)
-    a.dL_dscale, a.dL_drot, a.dL_dsemantic = dL_dscales.data_ptr(), dL_drot.data_ptr(), _ptr(dL_dsemantic)
+    a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = _ptr(dL_dmeans2D), _ptr(dL_dconic), dL_dopacity.data_ptr()
+    a.dL_dcolor, a.dL_ddepth, a.dL_dmean3D = _ptr(dL_dcolors), _ptr(dL_ddepths), dL_dmeans3D.data_ptr()
+    a.dL_dcov3D, a.dL_dsh = _ptr(dL_dcov3D), _ptr(dL_dsh)
+    a.dL_dscale, a.dL_drot, a.dL_dsemantic = _ptr(dL_dscales), _ptr(dL_drot), _ptr(dL_dsemantic)
     if _grad_rec is not None:
         grad_ws = _grad_rec.contiguous()
     else:
         grad_ws = torch.empty((P, 12), dtype=torch.float32, device=dev)
     a.grad_ws = grad_ws.data_ptr()
-    a.stream = _stream()
+    a.stream = _stream(dev)
     a.tile_row_stride, a.tile_row_phase = stride, phase
     a.stages, a.p_begin, a.p_count = int(_stage), p_begin, p_count
     if _peer_grad:

@@ -165,3 +165,10 @@ def load() -> C.CDLL:
 
 def last_error() -> str:
     return load().grpg_last_error().decode("utf-8", "replace")
+
+
+def current_stream_ptr(dev) -> int:
+    """Raw cudaStream_t of PyTorch's current stream on `dev` (the Stream-object route costs ~25 us per call)."""
+    import torch
+    idx = dev.index if getattr(dev, "index", None) is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)

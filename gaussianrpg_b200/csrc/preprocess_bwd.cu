@@ -71,11 +71,13 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     const float dcol[3] = {g1.w, g2.x, g2.y};
     const float ddep = g2.z;
 
-    dL_dmean2D[3 * idx] = dm2x; dL_dmean2D[3 * idx + 1] = dm2y; dL_dmean2D[3 * idx + 2] = dm2abs;
-    reinterpret_cast<float4*>(dL_dconic_out)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
+    // outputs nobody asked for (NULL) are not written: dL_dconic / dL_ddepth are internal to the chain rule, dL_dcolor
+    // only matters with precomputed colours, dL_dcov3D with precomputed covariances (56 of 168 B per Gaussian)
+    if (dL_dmean2D) { dL_dmean2D[3 * idx] = dm2x; dL_dmean2D[3 * idx + 1] = dm2y; dL_dmean2D[3 * idx + 2] = dm2abs; }
+    if (dL_dconic_out) reinterpret_cast<float4*>(dL_dconic_out)[idx] = make_float4(dcon_x, dcon_y, 0.f, dcon_w);
     dL_dopacity[idx] = dopac;
-    dL_dcolor[3 * idx] = dcol[0]; dL_dcolor[3 * idx + 1] = dcol[1]; dL_dcolor[3 * idx + 2] = dcol[2];
-    dL_ddepth[idx] = ddep;
+    if (dL_dcolor) { dL_dcolor[3 * idx] = dcol[0]; dL_dcolor[3 * idx + 1] = dcol[1]; dL_dcolor[3 * idx + 2] = dcol[2]; }
+    if (dL_ddepth) dL_ddepth[idx] = ddep;
 
     float dmean[3] = {0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -300,10 +302,12 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     }
 
     dL_dmean3D[3 * idx] = dmean[0]; dL_dmean3D[3 * idx + 1] = dmean[1]; dL_dmean3D[3 * idx + 2] = dmean[2];
+    if (dL_dcov3D) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
-    dL_dscale[3 * idx] = dscale[0]; dL_dscale[3 * idx + 1] = dscale[1]; dL_dscale[3 * idx + 2] = dscale[2];
-    reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
+    }
+    if (dL_dscale) { dL_dscale[3 * idx] = dscale[0]; dL_dscale[3 * idx + 1] = dscale[1]; dL_dscale[3 * idx + 2] = dscale[2]; }
+    if (dL_drot) reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
 }
 
 void launch_preprocess_bwd(const grpg_backward_args* a, const float* cov3D, const uint8_t* clamped,

@@ -51,7 +51,7 @@ def compose_rgb8(rgb: torch.Tensor, acc: Optional[torch.Tensor] = None, sky_colo
     a.sky = sky_c.data_ptr() if sky_c is not None else None
     a.out_rgb8 = out.data_ptr()
     a.out_rgb = outf.data_ptr() if outf is not None else None
-    a.stream = torch.cuda.current_stream(rgb.device).cuda_stream
+    a.stream = _lib.current_stream_ptr(rgb.device)
     with torch.cuda.device(rgb.device):
         if _lib.load().grpg_compose_rgb8(C.byref(a)) != 0:
             raise RuntimeError(_lib.last_error())

@@ -56,7 +56,7 @@ def _launch(img1, img2, mask, coef_l1: float, coef_ssim: float, want_grad: bool)
     args.coef_l1, args.coef_ssim = float(coef_l1), float(coef_ssim)
     args.sums = sums.data_ptr()
     args.grad = grad.data_ptr() if grad is not None else None
-    args.stream = torch.cuda.current_stream(img1.device).cuda_stream
+    args.stream = _lib.current_stream_ptr(img1.device)
     with torch.cuda.device(img1.device):
         _check(_lib.load().grpg_l1_ssim(C.byref(args)))
     return sums, grad, m

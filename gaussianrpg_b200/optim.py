@@ -78,7 +78,7 @@ def fused_adam_step(optimizers: Sequence[torch.optim.Adam]) -> int:
             t.step_size, t.bias_correction2_sqrt, t.eps = ss, bc2, eps
         ws = torch.empty(int(lib.grpg_adam_workspace_bytes(len(part))), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            if lib.grpg_adam_step(tab, len(part), ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream) != 0:
+            if lib.grpg_adam_step(tab, len(part), ws.data_ptr(), _lib.current_stream_ptr(dev)) != 0:
                 raise RuntimeError(_lib.last_error())
     return len(rows)
 
@@ -133,5 +133,5 @@ def update_densification_stats(stats: Sequence[DensifyStats], radii: torch.Tenso
     ws = torch.empty(int(lib.grpg_stats_workspace_bytes(len(stats))), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         if lib.grpg_densify_stats(tab, len(stats), r.data_ptr(), g.data_ptr(), ws.data_ptr(),
-                                  torch.cuda.current_stream(dev).cuda_stream) != 0:
+                                  _lib.current_stream_ptr(dev)) != 0:
             raise RuntimeError(_lib.last_error())

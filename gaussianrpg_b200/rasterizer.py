@@ -80,8 +80,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                        rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_color, grad_depth, grad_alpha,
                        grad_semantic, sh, rs.sh_degree, rs.campos, geom, ctx.num_rendered, binning, img, alpha,
                        semantics, rs.debug)
+        # inputs of forward(): means3D 0, means2D 1, sh 2, colors_precomp 3, semantics 4, opacities 5, scales 6,
+        # rotations 7, cov3Ds_precomp 8 -- gradients nobody needs are neither allocated nor written
+        need = ctx.needs_input_grad
+        wanted = (need[1], need[3], need[8], need[6] or need[7])
         (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot, g_sem) = _call_with_snapshot(
-            _C.rasterize_gaussians_backward, native_args, rs.debug, "snapshot_bw.dump", "backward")
+            lambda *a_: _C.rasterize_gaussians_backward(*a_, _wanted=wanted), native_args, rs.debug, "snapshot_bw.dump",
+            "backward")
         # order of forward()'s inputs: means3D, means2D, sh, colors_precomp, semantics, opacities, scales,
         # rotations, cov3Ds_precomp, raster_settings
         grads = (g_means3D, g_means2D, g_sh, g_colors, g_sem, g_opac, g_scales, g_rot, g_cov3D)

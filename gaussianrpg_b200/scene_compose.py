@@ -106,7 +106,7 @@ class _ComposeScene(torch.autograd.Function):
         desc = _descriptors(subs, is_actor, fourier, pose, idft_h, flips)
         with torch.cuda.device(dev):
             rc = lib.grpg_compose_forward(desc, n_sub, M, ws.data_ptr(), xyz.data_ptr(), rot.data_ptr(), scl.data_ptr(),
-                                          opa.data_ptr(), feat.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+                                          opa.data_ptr(), feat.data_ptr(), _lib.current_stream_ptr(dev))
         if rc != 0:
             raise RuntimeError(_lib.last_error())
         ctx.meta, ctx.subs, ctx.pose, ctx.desc = meta, subs, pose, desc
@@ -141,7 +141,7 @@ class _ComposeScene(torch.autograd.Function):
         with torch.cuda.device(dev):
             rc = lib.grpg_compose_backward(desc, n_sub, M, ws.data_ptr(), g_xyz.data_ptr(), g_rot.data_ptr(),
                                            g_scl.data_ptr(), g_opa.data_ptr(), g_feat.data_ptr(), d_rots.data_ptr(),
-                                           d_trans.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+                                           d_trans.data_ptr(), _lib.current_stream_ptr(dev))
         if rc != 0:
             raise RuntimeError(_lib.last_error())
         n_bk = n_sub - sum(is_actor)  # actors follow the background in the table

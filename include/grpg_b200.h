@@ -186,6 +186,7 @@ typedef struct grpg_backward_args {
     const float* dL_dpix_depth;   /* [1,H,W] */
     const float* dL_dalphas;      /* [1,H,W] */
     const float* dL_dpix_semantic;/* [S,H,W] or NULL */
+    /* dL_dmean2D, dL_dconic, dL_dcolor, dL_ddepth, dL_dcov3D, dL_dscale and dL_drot may be NULL: not written then */
     float* dL_dmean2D;            /* [P,3]  (x, y in NDC units, |x|+|y|)  backward.cu:625-628 */
     float* dL_dconic;             /* [P,4]  (.z unused, written 0)        backward.cu:633-635 */
     float* dL_dopacity;           /* [P,1] */
