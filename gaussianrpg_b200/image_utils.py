@@ -58,15 +58,26 @@ def compose_rgb8(rgb: torch.Tensor, acc: Optional[torch.Tensor] = None, sky_colo
     return out, outf
 
 
-def to_host_rgb8(rgb: torch.Tensor, acc: Optional[torch.Tensor] = None, sky_color: Optional[torch.Tensor] = None):
+def to_host_rgb8(rgb: torch.Tensor, acc: Optional[torch.Tensor] = None, sky_color: Optional[torch.Tensor] = None, *,
+                 direct: bool = False):
     """Drop-in for `(rgb.detach().cpu().numpy().transpose(1, 2, 0) * 255).astype(np.uint8)` (simulator.py:313-314),
     including the renderer's sky composite and clamp when `sky_color` is given.  Returns a numpy [H,W,3] uint8 view
-    of a pinned buffer that is reused by the next call with the same shape."""
+    of a pinned buffer that is reused by the next call with the same shape.
+
+    The kernel writes the interleaved bytes into a device buffer (7.4 MB at 1920x1280) and the copy engine moves them
+    to the pinned buffer; `direct=True` lets the kernel store straight into the pinned mapping instead (no device
+    buffer, but SM-issued PCIe writes: measured slower on B200 -- 1.1 ms vs 0.2 ms per frame)."""
     H, W = int(rgb.shape[1]), int(rgb.shape[2])
     key = (H, W, rgb.device.index)
-    buf = _pinned.get(key)
-    if buf is None:
-        buf = _pinned[key] = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True)
-    compose_rgb8(rgb, acc, sky_color, out=buf)
+    bufs = _pinned.get(key)
+    if bufs is None:
+        bufs = _pinned[key] = (torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True),
+                               torch.empty((H, W, 3), dtype=torch.uint8, device=rgb.device))
+    host, dev = bufs
+    if direct:
+        compose_rgb8(rgb, acc, sky_color, out=host)
+    else:
+        compose_rgb8(rgb, acc, sky_color, out=dev)
+        host.copy_(dev, non_blocking=True)
     torch.cuda.current_stream(rgb.device).synchronize()
-    return buf.numpy()
+    return host.numpy()

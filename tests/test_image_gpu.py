@@ -38,7 +38,9 @@ def test_bytes_bit_exact(H, W, with_sky, cuda_device):
     assert np.array_equal(out.cpu().numpy(), want)
     assert np.array_equal(outf.cpu().numpy(), wantf)
     host = image_utils.to_host_rgb8(rgb.to(d), acc.to(d) if with_sky else None, sky.to(d) if with_sky else None)
-    assert host.shape == (H, W, 3) and np.array_equal(host, want)  # stored by the kernel into pinned memory
+    assert host.shape == (H, W, 3) and np.array_equal(host, want)  # device bytes + copy engine
+    host = image_utils.to_host_rgb8(rgb.to(d), acc.to(d) if with_sky else None, sky.to(d) if with_sky else None, direct=True)
+    assert np.array_equal(host, want)  # stored by the kernel into pinned memory
 
 
 def test_exact_byte_boundaries(cuda_device):
