@@ -15,6 +15,8 @@ import torch
 from . import _lib
 
 NUM_CHANNELS = 3
+_NEED_BINNING = 2   # GRPG_NEED_BINNING (include/grpg_b200.h)
+_last_binned = {}    # (P, W, H, band, device) -> instances binned by the previous call: sizes the next workspace
 
 
 _cuda_ok = None
@@ -148,14 +150,27 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
         for i, ptr in enumerate(_peer_frames):
             a.peer_frames[i] = int(ptr)
 
+    # The binning workspace is sized by a device-side count.  Guess it from the previous call with the same shape
+    # (+25 %), so that both stages run inside one library call and the render stage is launched right behind the
+    # host sync; when the guess is too small the library stops after the geometry stage and the exact size is used.
+    key = (P, W, H, stride, phase, bool(_reference_binning), dev.index)
+    guess = _last_binned.get(key, 0)
+    bl = _lib.BinningLayout()
+    lib.grpg_get_binning_layout(int(guess * 1.25) + 4096, C.byref(bl))
+    binning = torch.empty(max(int(bl.total_bytes), 256), **u8)  # never empty: backward needs a valid pointer
+    a.binning_ws = _ptr(binning)
     with torch.cuda.device(dev):
         n_binned, n_rendered = C.c_int(0), C.c_int(0)
-        _check(lib.grpg_forward_geometry(C.byref(a), C.byref(n_binned), C.byref(n_rendered)))
-        bl = _lib.BinningLayout()
-        lib.grpg_get_binning_layout(int(n_binned.value), C.byref(bl))
-        binning = torch.empty(max(int(bl.total_bytes), 256), **u8)  # never empty: backward needs a valid pointer
-        a.binning_ws = _ptr(binning)
-        _check(lib.grpg_forward_render(C.byref(a), int(n_binned.value)))
+        rc = lib.grpg_forward(C.byref(a), binning.numel(), C.byref(n_binned), C.byref(n_rendered))
+        if rc == _NEED_BINNING:
+            lib.grpg_get_binning_layout(int(n_binned.value), C.byref(bl))
+            binning = torch.empty(max(int(bl.total_bytes), 256), **u8)
+            a.binning_ws = _ptr(binning)
+            rc = lib.grpg_forward_render(C.byref(a), int(n_binned.value))
+        _check(rc)
+    _last_binned[key] = int(n_binned.value)
+    if len(_last_binned) > 64:
+        _last_binned.pop(next(iter(_last_binned)))
     R = int(n_rendered.value)
     return R, out_color, out_depth, out_alpha, out_semantic, radii, geom, binning, img
 

@@ -256,6 +256,14 @@ int grpg_forward_render(const grpg_forward_args* a, int num_rendered) {
     return check_cuda("forward_render", a->debug != 0, stream);
 }
 
+int grpg_forward(const grpg_forward_args* a, size_t binning_capacity_bytes, int* num_binned, int* num_rendered) {
+    if (int rc = grpg_forward_geometry(a, num_binned, num_rendered)) return rc;
+    grpg_binning_layout BL;
+    grpg_get_binning_layout(*num_binned, &BL);
+    if (*num_binned > 0 && (!a->binning_ws || BL.total_bytes > binning_capacity_bytes)) return GRPG_NEED_BINNING;
+    return grpg_forward_render(a, *num_binned);
+}
+
 size_t grpg_backward_workspace_bytes(int P, int S) {
     (void)S;
     return align_up((size_t)P * 12 * sizeof(float), 256);

@@ -154,6 +154,13 @@ int grpg_forward_geometry(const grpg_forward_args* a, int* num_binned, int* num_
  * forward.cu:340-467). */
 int grpg_forward_render(const grpg_forward_args* a, int num_binned);
 
+/* Both stages in one call when the caller can guess the size of the binning workspace (e.g. from the previous
+ * frame): `a->binning_ws` holds `binning_capacity_bytes`.  If the instances fit, stage 2 is launched from inside the
+ * call, right behind the host sync, and 0 is returned.  If they do not, stage 1 is complete, GRPG_NEED_BINNING is
+ * returned and the caller allocates grpg_get_binning_layout(*num_binned) bytes and calls grpg_forward_render. */
+#define GRPG_NEED_BINNING 2
+int grpg_forward(const grpg_forward_args* a, size_t binning_capacity_bytes, int* num_binned, int* num_rendered);
+
 /* ------------------------------------------------------------------------- */
 /* Backward.  Replaces CudaRasterizer::Rasterizer::backward                   */
 /* (rasterizer.h:85-115, rasterizer_impl.cu:396-506) as bound by              */
