@@ -179,7 +179,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                  dL_dout_depth, dL_dout_alpha, dL_dout_semantic, sh, degree, campos, geomBuffer, R,
                                  binningBuffer, imageBuffer, alphas, semantics, debug, *, _band=(1, 0), _height=None,
-                                 _width=None, _stage=3, _grad_rec=None, _slice=None, _peer_grad=None, _wanted=None):
+                                 _width=None, _stage=3, _grad_rec=None, _slice=None, _peer_grad=None, _wanted=None,
+                                 _full_frame_grads=False):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:126-220).
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
@@ -193,6 +194,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     over the ranks while loading them instead of reading `_grad_rec`.  `_wanted=(means2D, colors, cov3D, scale_rot)`
     (booleans; the autograd function passes `ctx.needs_input_grad`) skips allocating and writing the outputs nobody
     reads -- they come back as None -- as well as the two internal ones (dL_dconic, dL_ddepth).
+    `_full_frame_grads=True` (with a band): the four pixel-gradient images are full frames [C,H,W], read by the kernel
+    at the band's true rows, instead of compact band images.
     """
     _require_cuda()
     lib = _lib.load()
@@ -271,6 +274,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     a.stream = _stream(dev)
     a.tile_row_stride, a.tile_row_phase = stride, phase
     a.stages, a.p_begin, a.p_count = int(_stage), p_begin, p_count
+    a.pixel_grads_full_frame = int(bool(_full_frame_grads))
     if _peer_grad:
         a.n_peer_grad = len(_peer_grad)
         for i, ptr in enumerate(_peer_grad):

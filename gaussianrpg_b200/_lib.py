@@ -61,6 +61,7 @@ class BackwardArgs(C.Structure):
         ("dL_dsemantic", _fp), ("grad_ws", _fp), ("stream", _fp),
         ("tile_row_stride", C.c_int), ("tile_row_phase", C.c_int), ("stages", C.c_int), ("p_begin", C.c_int),
         ("p_count", C.c_int), ("n_peer_grad", C.c_int), ("peer_grad_ws", _fp * 8),
+        ("pixel_grads_full_frame", C.c_int), ("reserved_", C.c_int),
     ]
 
 

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dpixel_depths, const float* __restrict__ dL_dalphas,
     const float* __restrict__ dL_dpixel_semantics, float* __restrict__ grad_rec /*[P][12]*/,
-    float* __restrict__ dL_dsemantics /*[P][S]*/, int HL, int row_stride, int row_phase) {
+    float* __restrict__ dL_dsemantics /*[P][S]*/, int HL, int row_stride, int row_phase, int grads_full) {
     // staged records (48-byte stride) and ids, double buffered and filled one batch ahead with cp.async
     // (see blend_fwd.cu)
     __shared__ __align__(16) float4 s_rec2[2][BWD_BATCH * 3];
@@ -76,8 +76,10 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     const bool inside = pix_x < W && pix_y < H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
     const float bx_lo = (float)bx0, bx_hi = (float)(bx0 + 7), by_lo = (float)by0, by_hi = (float)(by0 + 3);
-    const size_t hw = (size_t)HL * W;
     const size_t pid = (size_t)loc_y * W + pix_x;
+    // pixel gradients: band-compact like `alphas`, or full frames indexed by the true row
+    const size_t hw = grads_full ? (size_t)H * W : (size_t)HL * W;
+    const size_t gid_px = grads_full ? (size_t)pix_y * W + pix_x : pid;
 
     const uint2 range = ranges[tile];
     const int n_inst = (int)(range.y - range.x);
@@ -89,13 +91,13 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
     float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, dpix_depth = 0.f, dpix_alpha = 0.f;
     float dsem[SB > 0 ? SB : 1];
     if (inside) {
-        dpix0 = dL_dpixels[pid]; dpix1 = dL_dpixels[hw + pid]; dpix2 = dL_dpixels[2 * hw + pid];
-        dpix_depth = dL_dpixel_depths[pid];
-        dpix_alpha = dL_dalphas[pid];
+        dpix0 = dL_dpixels[gid_px]; dpix1 = dL_dpixels[hw + gid_px]; dpix2 = dL_dpixels[2 * hw + gid_px];
+        dpix_depth = dL_dpixel_depths[gid_px];
+        dpix_alpha = dL_dalphas[gid_px];
     }
 #pragma unroll
     for (int i = 0; i < (SB > 0 ? SB : 1); ++i)
-        dsem[i] = (SB > 0 && inside && i < S) ? dL_dpixel_semantics[(size_t)i * hw + pid] : 0.f;
+        dsem[i] = (SB > 0 && inside && i < S) ? dL_dpixel_semantics[(size_t)i * hw + gid_px] : 0.f;
     const float bg_dot_dpixel = bg_color[0] * dpix0 + bg_color[1] * dpix1 + bg_color[2] * dpix2;
 
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc_depth = 0.f, acc_alpha = 0.f;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
     const float* __restrict__ bg_color, const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
     const float* __restrict__ dL_dalphas, float* __restrict__ grad_rec /*[P][12]*/, int HL, int row_stride,
-    int row_phase) {
+    int row_phase, int grads_full) {
     constexpr int NT = 256 / PPL, NW = 8 / PPL, RPT = BWD_BATCH / NT;
     __shared__ __align__(16) float4 s_rec2[2][BWD_BATCH * 3];
     __shared__ uint32_t s_id2[2][BWD_BATCH];
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
     const int pix_x = bx0 + (lane & 7);
     const float pxf = (float)pix_x;
     const float bx_lo = (float)bx0, bx_hi = (float)(bx0 + 7), by_lo = (float)by0, by_hi = (float)(by0 + 4 * PPL - 1);
-    const size_t hw = (size_t)HL * W;
+    const size_t hw = grads_full ? (size_t)H * W : (size_t)HL * W;
 
     const uint2 range = ranges[tile];
     const int n_inst = (int)(range.y - range.x);
@@ -297,16 +299,17 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
         const int loc_y = blockIdx.y * GRPG_TILE + wy0 + (lane >> 3) + 4 * p;
         const bool inside = pix_x < W && pix_y < H;
         const size_t pid = (size_t)loc_y * W + pix_x;
+        const size_t gpx = grads_full ? (size_t)pix_y * W + pix_x : pid;
         pyf[p] = (float)pix_y;
         T_final[p] = inside ? 1.0f - alphas[pid] : 0.0f;
         T[p] = T_final[p];
         last_contributor[p] = inside ? (int)n_contrib[pid] : 0;
         lmax = max(lmax, last_contributor[p]);
-        dpix0[p] = inside ? dL_dpixels[pid] : 0.f;
-        dpix1[p] = inside ? dL_dpixels[hw + pid] : 0.f;
-        dpix2[p] = inside ? dL_dpixels[2 * hw + pid] : 0.f;
-        dpix_depth[p] = inside ? dL_dpixel_depths[pid] : 0.f;
-        dpix_alpha[p] = inside ? dL_dalphas[pid] : 0.f;
+        dpix0[p] = inside ? dL_dpixels[gpx] : 0.f;
+        dpix1[p] = inside ? dL_dpixels[hw + gpx] : 0.f;
+        dpix2[p] = inside ? dL_dpixels[2 * hw + gpx] : 0.f;
+        dpix_depth[p] = inside ? dL_dpixel_depths[gpx] : 0.f;
+        dpix_alpha[p] = inside ? dL_dalphas[gpx] : 0.f;
         bgdot[p] = bg0 * dpix0[p] + bg1 * dpix1[p] + bg2 * dpix2[p];
         acc0[p] = acc1[p] = acc2[p] = acc_depth[p] = acc_alpha[p] = 0.f;
         lastc0[p] = lastc1[p] = lastc2[p] = last_depth[p] = last_alpha[p] = 0.f;
@@ -472,16 +475,17 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
     const dim3 grid((a->width + GRPG_TILE - 1) / GRPG_TILE, band_rows(a->height, stride, phase), 1);
     if (grid.y == 0) return;
     const int S = a->S;
+    const int gfull = (stride > 1 && a->pixel_grads_full_frame) ? 1 : 0;
     ProfScope ps("blend_bwd", stream);
 #define GRPG_BWD_LAUNCH(SBV)                                                                                      \
     blend_bwd_kernel<SBV><<<grid, 256, 0, stream>>>(ranges, point_list, rec, a->semantics, S, a->width, a->height,  \
                                                      a->background, a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth, \
-                                                     a->dL_dalphas, a->dL_dpix_semantic, grad_rec, a->dL_dsemantic, HL, stride, phase)
+                                                     a->dL_dalphas, a->dL_dpix_semantic, grad_rec, a->dL_dsemantic, HL, stride, phase, gfull)
     const int ppl = S == 0 ? bwd_pixels_per_lane() : 1;
 #define GRPG_BWD_WIDE(PPLV, MINBV)                                                                                         \
     blend_bwd_wide_kernel<PPLV, MINBV><<<grid, 256 / PPLV, 0, stream>>>(ranges, point_list, rec, a->width, a->height,      \
                                                                  a->background, a->alphas, n_contrib, a->dL_dpix,    \
-                                                                 a->dL_dpix_depth, a->dL_dalphas, grad_rec, HL, stride, phase)
+                                                                 a->dL_dpix_depth, a->dL_dalphas, grad_rec, HL, stride, phase, gfull)
     if (ppl == 2) GRPG_BWD_WIDE(2, 5);  // 95 registers, 5 CTAs of 4 warps per SM: the measured optimum (4: 1.17 ms, 5: 1.08, 6-7: 1.09, 8: 1.28)
     else if (S == 0) GRPG_BWD_LAUNCH(0);
     else if (S <= 4) GRPG_BWD_LAUNCH(4);

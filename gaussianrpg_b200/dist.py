@@ -211,7 +211,7 @@ class _ShardedRasterize(torch.autograd.Function):
         H, W = rs.image_height, rs.image_width
         P = means3D.shape[0]
         S = g_sem.shape[0]
-        gb = frame_to_band(torch.cat([g_color, g_depth, g_alpha, g_sem], 0), k, r)
+        # the blend backward reads the band's rows straight out of the full-frame loss gradients
         common = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                   rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy)
         tail = (sh, rs.sh_degree, rs.campos, geom, ctx.R, binning, img, alpha_b, semantics, rs.debug)
@@ -220,8 +220,9 @@ class _ShardedRasterize(torch.autograd.Function):
                 and dist.get_backend(group) == "nccl"):
             peer_rec = _PeerRecords.get(P, means3D.device, group)
         grad_rec, g_semantics = _C.rasterize_gaussians_backward(
-            *common, gb[:3].contiguous(), gb[3:4].contiguous(), gb[4:5].contiguous(), gb[5:5 + S].contiguous(), *tail,
-            _band=(k, r), _height=H, _width=W, _stage=1, _grad_rec=peer_rec.rec if peer_rec is not None else None)
+            *common, g_color.contiguous(), g_depth.contiguous(), g_alpha.contiguous(), g_sem.contiguous(), *tail,
+            _band=(k, r), _height=H, _width=W, _stage=1, _full_frame_grads=True,
+            _grad_rec=peer_rec.rec if peer_rec is not None else None)
         # Sum the per-Gaussian 2D gradient records over ranks.  Two exchange plans:
         #  "shard":     reduce-scatter the 48 B records, per-Gaussian backward on the owned slice, all-gather the
         #               parameter-gradient shards (104 B per Gaussian for means/sh/opacity/scale/rotation);
@@ -357,6 +358,28 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
     for _ in range(2):
         e2e()
     ms_e2e = timed(e2e, args.steps)
+    # camera-parallel companion line ("pure camera-parallel ... should be reported beside it"): every rank
+    # renders its OWN camera of a batch of `world` cameras with the single-GPU operator, no exchange at all
+    from .rasterizer import GaussianRasterizer
+    solo = GaussianRasterizer(sc.settings())
+
+    def solo_fwd_bwd():
+        for v in leaves.values():
+            v.grad = None
+        means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
+        color, radii, depth, alpha, _ = solo(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+                                             shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+        ((color - gt).abs().mean() + (depth * w_depth).mean() + (alpha * w_alpha).mean()).backward()
+
+    def solo_fwd():
+        with torch.no_grad():
+            solo(means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"], shs=leaves["shs"],
+                 scales=leaves["scales"], rotations=leaves["rotations"])
+
+    for _ in range(3):
+        solo_fwd_bwd(); solo_fwd()
+    ms_solo_fb = timed(solo_fwd_bwd, args.steps)
+    ms_solo_f = timed(solo_fwd, args.steps)
     band_bytes = 5 * max_band_rows(H, world) * TILE * W * 4
     return {
         "metric": "iters_per_sec_fwd_bwd_1920x1280_2M", "value": 1000.0 * args.steps / ms_fb, "unit": "iters/s",
@@ -366,6 +389,10 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
         "e2e": {"value": 1000.0 * args.steps / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": int(gt_host.numel() * 4),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": 16 * args.steps,
+        "camera_parallel": {"value": 1000.0 * args.steps * world / ms_solo_fb, "unit": "iters/s",
+                            "fwd_fps": 1000.0 * args.steps * world / ms_solo_f, "scaling": "weak",
+                            "note": f"a batch of {world} cameras, one per GPU, single-GPU operator, no exchange "
+                                    f"(the upper bound SURVEY 8e asks to report beside the sharded number)"},
         "config": {"workload": f"street scene {P} Gaussians, {W}x{H}, fwd+bwd, one frame split over {world} GPUs",
                    "parallelism": f"tile rows interleaved mod {world} (fwd, all-gather {band_bytes} B/rank) + "
                                   f"all-reduce (reduce-scatter + all-gather) of the 48 B per-Gaussian gradient records "

@@ -224,6 +224,11 @@ typedef struct grpg_backward_args {
      * is reused before every rank's stage 2 has finished. */
     int n_peer_grad;
     const float* peer_grad_ws[8];
+    /* With a band (tile_row_stride > 1): non-zero = dL_dpix, dL_dpix_depth, dL_dalphas, dL_dpix_semantic are FULL
+     * frames [C,H,W] indexed by the true pixel row (the caller need not cut the band out of the loss gradient);
+     * `alphas` keeps the compact band layout of the forward call either way. */
+    int pixel_grads_full_frame;
+    int reserved_;
 } grpg_backward_args;
 
 size_t grpg_backward_workspace_bytes(int P, int S);

@@ -132,3 +132,26 @@ def test_misaligned_views_take_the_plain_load_path(cuda_device):
     other = GaussianRasterizer(sc.settings())(means2D=None, **kw)
     for a, b in zip(base, other):
         assert torch.equal(a, b)
+
+
+def test_binning_workspace_guess_too_small_and_too_large(cuda_device):
+    """The binning workspace is sized from the previous call with the same shape (grpg_forward); a guess that is too
+    small must fall back to the exact two-stage path, a guess that is far too large must change nothing."""
+    from gaussianrpg_b200 import _C
+    import cases
+    small = synthetic.plumbing_scene(P=3000, W=320, H=192, seed=3)
+    big = synthetic.plumbing_scene(P=3000, W=320, H=192, seed=4)
+    small.scales = small.scales * 0.2
+    big.scales = big.scales * 4.0  # same shape, several times the instances (the guess carries 25 % slack)
+    outs = {}
+    for name, order in (("big_after_small", (small, big)), ("big_alone", (big,)), ("small_after_big", (big, small)),
+                        ("small_alone", (small,))):
+        _C._last_binned.clear()
+        for sc in order:
+            fwd = cases.raw_forward(_C, sc.to(cuda_device))
+        outs[name] = fwd
+    assert outs["big_after_small"][0] > 2 * outs["small_alone"][0]
+    for a, b in (("big_after_small", "big_alone"), ("small_after_big", "small_alone")):
+        assert outs[a][0] == outs[b][0]
+        for i in (1, 2, 3, 5):
+            assert torch.equal(outs[a][i], outs[b][i]), (a, i)
