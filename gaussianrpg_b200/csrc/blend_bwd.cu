@@ -100,11 +100,12 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
         dsem[i] = (SB > 0 && inside && i < S) ? dL_dpixel_semantics[(size_t)i * hw + gid_px] : 0.f;
     const float bg_dot_dpixel = bg_color[0] * dpix0 + bg_color[1] * dpix1 + bg_color[2] * dpix2;
 
+    // the reference's "last contributor" recurrences (backward.cu:560-601) are applied eagerly, right after a Gaussian
+    // has been handled, so last_alpha / last_color / last_depth / last_semantic need not be carried (see the wide kernel)
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc_depth = 0.f, acc_alpha = 0.f;
-    float lastc0 = 0.f, lastc1 = 0.f, lastc2 = 0.f, last_depth = 0.f, last_alpha = 0.f;
-    float acc_sem[SB > 0 ? SB : 1], last_sem[SB > 0 ? SB : 1];
+    float acc_sem[SB > 0 ? SB : 1];
 #pragma unroll
-    for (int i = 0; i < (SB > 0 ? SB : 1); ++i) { acc_sem[i] = 0.f; last_sem[i] = 0.f; }
+    for (int i = 0; i < (SB > 0 ? SB : 1); ++i) acc_sem[i] = 0.f;
 
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     // record component this lane owns after warp_reduce12 (11 = nothing)
@@ -196,30 +197,29 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha));
                     T = T * inv_1ma;
                     const float w_at = alpha * T;
+                    const float one_m_al = 1.f - alpha;
                     float dL_dopa = 0.f;
-                    acc0 = last_alpha * lastc0 + (1.f - last_alpha) * acc0; lastc0 = c.x;
                     dL_dopa += (c.x - acc0) * dpix0; g_c0 = w_at * dpix0;
-                    acc1 = last_alpha * lastc1 + (1.f - last_alpha) * acc1; lastc1 = c.y;
                     dL_dopa += (c.y - acc1) * dpix1; g_c1 = w_at * dpix1;
-                    acc2 = last_alpha * lastc2 + (1.f - last_alpha) * acc2; lastc2 = c.z;
                     dL_dopa += (c.z - acc2) * dpix2; g_c2 = w_at * dpix2;
+                    acc0 = __fmaf_rn(alpha, c.x, one_m_al * acc0);
+                    acc1 = __fmaf_rn(alpha, c.y, one_m_al * acc1);
+                    acc2 = __fmaf_rn(alpha, c.z, one_m_al * acc2);
                     if (SB > 0) {
 #pragma unroll
                         for (int i = 0; i < SB; ++i) {
                             if (i < S) {
-                                acc_sem[i] = last_alpha * last_sem[i] + (1.f - last_alpha) * acc_sem[i];
-                                last_sem[i] = sv[i];
                                 dL_dopa += (sv[i] - acc_sem[i]) * dsem[i];
                                 g_sem[i] = w_at * dsem[i];
+                                acc_sem[i] = __fmaf_rn(alpha, sv[i], one_m_al * acc_sem[i]);
                             }
                         }
                     }
-                    acc_depth = last_alpha * last_depth + (1.f - last_alpha) * acc_depth; last_depth = c.w;
                     dL_dopa += (c.w - acc_depth) * dpix_depth; g_d = w_at * dpix_depth;
-                    acc_alpha = last_alpha + (1.f - last_alpha) * acc_alpha;
+                    acc_depth = __fmaf_rn(alpha, c.w, one_m_al * acc_depth);
                     dL_dopa += (1.f - acc_alpha) * dpix_alpha;
+                    acc_alpha = __fmaf_rn(one_m_al, acc_alpha, alpha);
                     dL_dopa *= T;
-                    last_alpha = alpha;
                     dL_dopa += (-T_final * inv_1ma) * bg_dot_dpixel;
 
                     const float dL_dG = b.w * dL_dopa;
@@ -288,9 +288,13 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
     const int n_inst = (int)(range.y - range.x);
     const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 
-    float pyf[PPL], T[PPL], T_final[PPL], dpix0[PPL], dpix1[PPL], dpix2[PPL], dpix_depth[PPL], dpix_alpha[PPL], bgdot[PPL];
+    // per-pixel state: 13 registers.  The reference's "last contributor" recurrences (backward.cu:560-601:
+    // acc = last_alpha * last_c + (1 - last_alpha) * acc, evaluated when the NEXT Gaussian arrives) are applied eagerly,
+    // right after a Gaussian has been handled -- the same operations on the same values one step earlier -- so the five
+    // last_* values never have to be carried.
+    float pyf[PPL], T[PPL], tfb[PPL] /* T_final * (bg . dL_dpixel) */, dpix0[PPL], dpix1[PPL], dpix2[PPL], dpix_depth[PPL],
+        dpix_alpha[PPL];
     float acc0[PPL], acc1[PPL], acc2[PPL], acc_depth[PPL], acc_alpha[PPL];
-    float lastc0[PPL], lastc1[PPL], lastc2[PPL], last_depth[PPL], last_alpha[PPL];
     int last_contributor[PPL];
     int lmax = 0;
 #pragma unroll
@@ -301,8 +305,7 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
         const size_t pid = (size_t)loc_y * W + pix_x;
         const size_t gpx = grads_full ? (size_t)pix_y * W + pix_x : pid;
         pyf[p] = (float)pix_y;
-        T_final[p] = inside ? 1.0f - alphas[pid] : 0.0f;
-        T[p] = T_final[p];
+        T[p] = inside ? 1.0f - alphas[pid] : 0.0f;  // T_final (backward.cu:468)
         last_contributor[p] = inside ? (int)n_contrib[pid] : 0;
         lmax = max(lmax, last_contributor[p]);
         dpix0[p] = inside ? dL_dpixels[gpx] : 0.f;
@@ -310,9 +313,8 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
         dpix2[p] = inside ? dL_dpixels[2 * hw + gpx] : 0.f;
         dpix_depth[p] = inside ? dL_dpixel_depths[gpx] : 0.f;
         dpix_alpha[p] = inside ? dL_dalphas[gpx] : 0.f;
-        bgdot[p] = bg0 * dpix0[p] + bg1 * dpix1[p] + bg2 * dpix2[p];
+        tfb[p] = T[p] * (bg0 * dpix0[p] + bg1 * dpix1[p] + bg2 * dpix2[p]);
         acc0[p] = acc1[p] = acc2[p] = acc_depth[p] = acc_alpha[p] = 0.f;
-        lastc0[p] = lastc1[p] = lastc2[p] = last_depth[p] = last_alpha[p] = 0.f;
     }
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     const int red_sub = ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
@@ -414,21 +416,20 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha[p]));
                     T[p] = T[p] * inv_1ma;
                     const float w_at = alpha[p] * T[p];
-                    const float la = last_alpha[p], one_m_la = 1.f - la;
-                    float dL_dopa = 0.f;
-                    acc0[p] = la * lastc0[p] + one_m_la * acc0[p]; lastc0[p] = c.x;
-                    dL_dopa += (c.x - acc0[p]) * dpix0[p];
-                    acc1[p] = la * lastc1[p] + one_m_la * acc1[p]; lastc1[p] = c.y;
+                    float dL_dopa = (c.x - acc0[p]) * dpix0[p];
                     dL_dopa += (c.y - acc1[p]) * dpix1[p];
-                    acc2[p] = la * lastc2[p] + one_m_la * acc2[p]; lastc2[p] = c.z;
                     dL_dopa += (c.z - acc2[p]) * dpix2[p];
-                    acc_depth[p] = la * last_depth[p] + one_m_la * acc_depth[p]; last_depth[p] = c.w;
                     dL_dopa += (c.w - acc_depth[p]) * dpix_depth[p];
-                    acc_alpha[p] = la + one_m_la * acc_alpha[p];
                     dL_dopa += (1.f - acc_alpha[p]) * dpix_alpha[p];
                     dL_dopa *= T[p];
-                    last_alpha[p] = alpha[p];
-                    dL_dopa += (-T_final[p] * inv_1ma) * bgdot[p];
+                    dL_dopa += -(tfb[p] * inv_1ma);
+                    // eager recurrences for the next (nearer) Gaussian of this pixel
+                    const float al = alpha[p], one_m_al = 1.f - al;
+                    acc0[p] = __fmaf_rn(al, c.x, one_m_al * acc0[p]);
+                    acc1[p] = __fmaf_rn(al, c.y, one_m_al * acc1[p]);
+                    acc2[p] = __fmaf_rn(al, c.z, one_m_al * acc2[p]);
+                    acc_depth[p] = __fmaf_rn(al, c.w, one_m_al * acc_depth[p]);
+                    acc_alpha[p] = __fmaf_rn(one_m_al, acc_alpha[p], al);
 
                     const float dL_dG = b.w * dL_dopa;
                     const float gdx = G[p] * dx, gdy = G[p] * dy[p];
@@ -486,7 +487,7 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
     blend_bwd_wide_kernel<PPLV, MINBV><<<grid, 256 / PPLV, 0, stream>>>(ranges, point_list, rec, a->width, a->height,      \
                                                                  a->background, a->alphas, n_contrib, a->dL_dpix,    \
                                                                  a->dL_dpix_depth, a->dL_dalphas, grad_rec, HL, stride, phase, gfull)
-    if (ppl == 2) GRPG_BWD_WIDE(2, 5);  // 95 registers, 5 CTAs of 4 warps per SM: the measured optimum (4: 1.17 ms, 5: 1.08, 6-7: 1.09, 8: 1.28)
+    if (ppl == 2) GRPG_BWD_WIDE(2, 7);  // 71 registers, 7 CTAs of 4 warps per SM: measured 5: 1.058 ms, 6: 1.022, 7: 1.017, 8 (spills): 1.027
     else if (S == 0) GRPG_BWD_LAUNCH(0);
     else if (S <= 4) GRPG_BWD_LAUNCH(4);
     else if (S <= 8) GRPG_BWD_LAUNCH(8);
