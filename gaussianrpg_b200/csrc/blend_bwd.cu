@@ -100,12 +100,9 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
         dsem[i] = (SB > 0 && inside && i < S) ? dL_dpixel_semantics[(size_t)i * hw + gid_px] : 0.f;
     const float bg_dot_dpixel = bg_color[0] * dpix0 + bg_color[1] * dpix1 + bg_color[2] * dpix2;
 
-    // the reference's "last contributor" recurrences (backward.cu:560-601) are applied eagerly, right after a Gaussian
-    // has been handled, so last_alpha / last_color / last_depth / last_semantic need not be carried (see the wide kernel)
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc_depth = 0.f, acc_alpha = 0.f;
-    float acc_sem[SB > 0 ? SB : 1];
-#pragma unroll
-    for (int i = 0; i < (SB > 0 ? SB : 1); ++i) acc_sem[i] = 0.f;
+    // the reference's per-channel "last contributor" recurrences (backward.cu:560-604) collapse into one scalar: see
+    // the wide kernel below (A <- a_k s_k + (1 - a_k) A with s_k = sum_u u_k g_u, dL/da = s_k - A)
+    float accA = 0.f;
 
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     // record component this lane owns after warp_reduce12 (11 = nothing)
@@ -197,29 +194,20 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha));
                     T = T * inv_1ma;
                     const float w_at = alpha * T;
-                    const float one_m_al = 1.f - alpha;
-                    float dL_dopa = 0.f;
-                    dL_dopa += (c.x - acc0) * dpix0; g_c0 = w_at * dpix0;
-                    dL_dopa += (c.y - acc1) * dpix1; g_c1 = w_at * dpix1;
-                    dL_dopa += (c.z - acc2) * dpix2; g_c2 = w_at * dpix2;
-                    acc0 = __fmaf_rn(alpha, c.x, one_m_al * acc0);
-                    acc1 = __fmaf_rn(alpha, c.y, one_m_al * acc1);
-                    acc2 = __fmaf_rn(alpha, c.z, one_m_al * acc2);
+                    float s_k = __fmaf_rn(c.z, dpix2, __fmaf_rn(c.y, dpix1, __fmaf_rn(c.x, dpix0, dpix_alpha)));
+                    g_c0 = w_at * dpix0; g_c1 = w_at * dpix1; g_c2 = w_at * dpix2;
                     if (SB > 0) {
 #pragma unroll
                         for (int i = 0; i < SB; ++i) {
                             if (i < S) {
-                                dL_dopa += (sv[i] - acc_sem[i]) * dsem[i];
+                                s_k = __fmaf_rn(sv[i], dsem[i], s_k);
                                 g_sem[i] = w_at * dsem[i];
-                                acc_sem[i] = __fmaf_rn(alpha, sv[i], one_m_al * acc_sem[i]);
                             }
                         }
                     }
-                    dL_dopa += (c.w - acc_depth) * dpix_depth; g_d = w_at * dpix_depth;
-                    acc_depth = __fmaf_rn(alpha, c.w, one_m_al * acc_depth);
-                    dL_dopa += (1.f - acc_alpha) * dpix_alpha;
-                    acc_alpha = __fmaf_rn(one_m_al, acc_alpha, alpha);
-                    dL_dopa *= T;
+                    s_k = __fmaf_rn(c.w, dpix_depth, s_k); g_d = w_at * dpix_depth;
+                    float dL_dopa = (s_k - accA) * T;
+                    accA = __fmaf_rn(alpha, s_k, (1.f - alpha) * accA);
                     dL_dopa += (-T_final * inv_1ma) * bg_dot_dpixel;
 
                     const float dL_dG = b.w * dL_dopa;
@@ -288,13 +276,15 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
     const int n_inst = (int)(range.y - range.x);
     const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 
-    // per-pixel state: 13 registers.  The reference's "last contributor" recurrences (backward.cu:560-601:
-    // acc = last_alpha * last_c + (1 - last_alpha) * acc, evaluated when the NEXT Gaussian arrives) are applied eagerly,
-    // right after a Gaussian has been handled -- the same operations on the same values one step earlier -- so the five
-    // last_* values never have to be carried.
+    // Per-pixel state: 9 registers.  The reference carries, per channel u (3 colours, depth, alpha with u_k = 1), the
+    // recurrence acc_u <- a_last u_last + (1 - a_last) acc_u and forms dL/da = sum_u (u_k - acc_u) g_u
+    // (backward.cu:560-604).  Only the g-weighted sum of the acc_u is ever used, and it obeys the same recurrence:
+    // with s_k = sum_u u_k g_u,  A <- a_k s_k + (1 - a_k) A  and  dL/da = s_k - A.  One scalar replaces five (and the
+    // five "last" values), 7 instead of 20 instructions per pixel and Gaussian; rounding is of the same order as the
+    // reference's own (each acc_u carries the rounding of its recurrence too).
     float pyf[PPL], T[PPL], tfb[PPL] /* T_final * (bg . dL_dpixel) */, dpix0[PPL], dpix1[PPL], dpix2[PPL], dpix_depth[PPL],
         dpix_alpha[PPL];
-    float acc0[PPL], acc1[PPL], acc2[PPL], acc_depth[PPL], acc_alpha[PPL];
+    float accA[PPL];
     int last_contributor[PPL];
     int lmax = 0;
 #pragma unroll
@@ -314,7 +304,7 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
         dpix_depth[p] = inside ? dL_dpixel_depths[gpx] : 0.f;
         dpix_alpha[p] = inside ? dL_dalphas[gpx] : 0.f;
         tfb[p] = T[p] * (bg0 * dpix0[p] + bg1 * dpix1[p] + bg2 * dpix2[p]);
-        acc0[p] = acc1[p] = acc2[p] = acc_depth[p] = acc_alpha[p] = 0.f;
+        accA[p] = 0.f;
     }
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     const int red_sub = ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
@@ -416,20 +406,11 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1ma) : "f"(1.f - alpha[p]));
                     T[p] = T[p] * inv_1ma;
                     const float w_at = alpha[p] * T[p];
-                    float dL_dopa = (c.x - acc0[p]) * dpix0[p];
-                    dL_dopa += (c.y - acc1[p]) * dpix1[p];
-                    dL_dopa += (c.z - acc2[p]) * dpix2[p];
-                    dL_dopa += (c.w - acc_depth[p]) * dpix_depth[p];
-                    dL_dopa += (1.f - acc_alpha[p]) * dpix_alpha[p];
-                    dL_dopa *= T[p];
+                    const float s_k = __fmaf_rn(c.w, dpix_depth[p], __fmaf_rn(c.z, dpix2[p], __fmaf_rn(c.y, dpix1[p],
+                                                __fmaf_rn(c.x, dpix0[p], dpix_alpha[p]))));
+                    float dL_dopa = (s_k - accA[p]) * T[p];
                     dL_dopa += -(tfb[p] * inv_1ma);
-                    // eager recurrences for the next (nearer) Gaussian of this pixel
-                    const float al = alpha[p], one_m_al = 1.f - al;
-                    acc0[p] = __fmaf_rn(al, c.x, one_m_al * acc0[p]);
-                    acc1[p] = __fmaf_rn(al, c.y, one_m_al * acc1[p]);
-                    acc2[p] = __fmaf_rn(al, c.z, one_m_al * acc2[p]);
-                    acc_depth[p] = __fmaf_rn(al, c.w, one_m_al * acc_depth[p]);
-                    acc_alpha[p] = __fmaf_rn(one_m_al, acc_alpha[p], al);
+                    accA[p] = __fmaf_rn(alpha[p], s_k, (1.f - alpha[p]) * accA[p]);  // for the next (nearer) Gaussian
 
                     const float dL_dG = b.w * dL_dopa;
                     const float gdx = G[p] * dx, gdy = G[p] * dy[p];
@@ -487,7 +468,7 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
     blend_bwd_wide_kernel<PPLV, MINBV><<<grid, 256 / PPLV, 0, stream>>>(ranges, point_list, rec, a->width, a->height,      \
                                                                  a->background, a->alphas, n_contrib, a->dL_dpix,    \
                                                                  a->dL_dpix_depth, a->dL_dalphas, grad_rec, HL, stride, phase, gfull)
-    if (ppl == 2) GRPG_BWD_WIDE(2, 7);  // 71 registers, 7 CTAs of 4 warps per SM: measured 5: 1.058 ms, 6: 1.022, 7: 1.017, 8 (spills): 1.027
+    if (ppl == 2) GRPG_BWD_WIDE(2, 7);  // 72 registers, 7 CTAs of 4 warps per SM (measured 6: 0.911 ms, 7: 0.912, 8: 0.931)
     else if (S == 0) GRPG_BWD_LAUNCH(0);
     else if (S <= 4) GRPG_BWD_LAUNCH(4);
     else if (S <= 8) GRPG_BWD_LAUNCH(8);
