@@ -309,6 +309,8 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     const int red_sub = ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     const int red_slot = red_sub < 3 ? ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + red_sub : 11;
+    // factor applied to the warp total of the slot this lane ends up owning (see the per-pixel section)
+    const float slot_scale = red_slot == 0 ? -ddelx_dx : red_slot == 1 ? -ddely_dy : (red_slot >= 3 && red_slot <= 5) ? -0.5f : 1.0f;
 
     const int wmax = __reduce_max_sync(0xffffffffu, lmax);
     if (lane == 0) s_maxlast[warp] = wmax;
@@ -412,27 +414,26 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
                     dL_dopa += -(tfb[p] * inv_1ma);
                     accA[p] = __fmaf_rn(alpha[p], s_k, (1.f - alpha[p]) * accA[p]);  // for the next (nearer) Gaussian
 
-                    const float dL_dG = b.w * dL_dopa;
-                    const float gdx = G[p] * dx, gdy = G[p] * dy[p];
-                    const float dG_ddelx = -gdx * b.x - gdy * b.y;
-                    const float dG_ddely = -gdy * b.z - gdx * b.y;
-                    const float g_mx = dL_dG * dG_ddelx * ddelx_dx;
-                    const float g_my = dL_dG * dG_ddely * ddely_dy;
-                    vals[0] += g_mx;
-                    vals[1] += g_my;
-                    vals[2] += fabsf(g_mx) + fabsf(g_my);
-                    const float hG = -0.5f * dL_dG;
-                    vals[3] += hG * gdx * dx;
-                    vals[4] += hG * gdx * dy[p];
-                    vals[5] += hG * gdy * dy[p];
-                    vals[6] += G[p] * dL_dopa;
+                    // With u = dL/dG * G * dx and v = dL/dG * G * dy the mean gradients are -(uA + vB) 0.5W and
+                    // -(vC + uB) 0.5H and the conic gradients -0.5 (u dx, u dy, v dy): the per-Gaussian constants
+                    // (0.5W, 0.5H, -0.5, the signs) are applied once to the warp sums (slot_scale), not per pixel.
+                    const float uG = (b.w * dL_dopa) * G[p];
+                    const float u = uG * dx, v = uG * dy[p];
+                    const float px_ = __fmaf_rn(u, b.x, v * b.y), py_ = __fmaf_rn(v, b.z, u * b.y);
+                    vals[0] += px_;
+                    vals[1] += py_;
+                    vals[2] = __fmaf_rn(fabsf(px_), ddelx_dx, __fmaf_rn(fabsf(py_), ddely_dy, vals[2]));
+                    vals[3] = __fmaf_rn(u, dx, vals[3]);
+                    vals[4] = __fmaf_rn(u, dy[p], vals[4]);
+                    vals[5] = __fmaf_rn(v, dy[p], vals[5]);
+                    vals[6] = __fmaf_rn(G[p], dL_dopa, vals[6]);
                     vals[7] += w_at * dpix0[p];
                     vals[8] += w_at * dpix1[p];
                     vals[9] += w_at * dpix2[p];
                     vals[10] += w_at * dpix_depth[p];
                 }
             }
-            const float mine = warp_reduce12(vals, lane);
+            const float mine = warp_reduce12(vals, lane) * slot_scale;
             if (!(lane & 1) && red_slot < 11) atomicAdd(grad_rec + (size_t)gid * GREC + red_slot, mine);
         }
     }
