@@ -14,8 +14,15 @@ SHAPES = lambda n, M, F: dict(xyz=(n, 3), features_dc=(n, F, 3), features_rest=(
                               scaling=(n, 3), rotation=(n, 4), semantic=(n, 0))
 
 
+class _Cfg(types.SimpleNamespace):
+    """attribute access plus `.get(key, default)`, like the reference's yacs CfgNode"""
+
+    def get(self, key, default=None):
+        return getattr(self, key, default)
+
+
 def optim_namespace():
-    return types.SimpleNamespace(**OPTIM_CFG)
+    return _Cfg(**OPTIM_CFG)
 
 
 def adam_cases():
