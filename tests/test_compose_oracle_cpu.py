@@ -50,3 +50,20 @@ def test_idft_base_matches_reference_lines():
     t = 0.37
     want = [1.0, np.sin(np.pi * t * 2), np.cos(np.pi * t * 2), np.sin(np.pi * t * 4), np.cos(np.pi * t * 4)]
     assert np.allclose(b, want, atol=1e-6)
+
+
+def test_street_scene_graph_composes_back_to_the_scene():
+    """gaussianrpg_b200.synthetic.street_scene_graph (the sub-model form of BASELINE config #3 used by
+    tools/train_iter_bench.py) must compose, by the reference's rules, into exactly the rasterizer inputs of
+    synthetic.street_scene."""
+    import torch
+    from gaussianrpg_b200 import synthetic
+    sc = synthetic.street_scene(P=120_000, n_actors=8, actor_points=2_000)
+    bk, actors, rots, trans, idft = synthetic.street_scene_graph(sc)
+    assert bk["xyz"].shape[0] == sc.extra["n_bkgd"] and len(actors) == 8 and actors[0]["features_dc"].shape[1] == 5
+    np_ = lambda d: {k: v.numpy() for k, v in d.items()}  # noqa: E731
+    out = compose_oracle.compose(np_(bk), [np_(a) for a in actors], rots.numpy(), trans.numpy(), idft,
+                                 [np.zeros(a["xyz"].shape[0], dtype=bool) for a in actors])
+    for k, ref in (("xyz", sc.means3D), ("rotation", sc.rotations), ("scaling", sc.scales), ("opacity", sc.opacities),
+                   ("features", sc.shs)):
+        assert np.abs(out[k] - ref.numpy()).max() <= 5e-6 * max(1.0, float(ref.abs().max())), k
