@@ -388,7 +388,9 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
         "impl": "ours", "fwd_fps": 1000.0 * args.steps / ms_f,
         "e2e": {"value": 1000.0 * args.steps / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": int(gt_host.numel() * 4),
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": 16 * args.steps,
+        # kernels of this library per step and rank: 22 forward (preprocess, 12 depth-sort, scan, emit, 5 tile-sort,
+        # ranges, blend) + 2 backward -- the count bench.py measures with the library's profiler on one GPU
+        "gpu_launches": 24 * args.steps * world,
         "camera_parallel": {"value": 1000.0 * args.steps * world / ms_solo_fb, "unit": "iters/s",
                             "fwd_fps": 1000.0 * args.steps * world / ms_solo_f, "scaling": "weak",
                             "note": f"a batch of {world} cameras, one per GPU, single-GPU operator, no exchange "
