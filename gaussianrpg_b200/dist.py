@@ -20,8 +20,7 @@ The pure tensor helpers (band <-> frame, slices) are device-agnostic and are wha
 """
 from __future__ import annotations
 
-import math
-from typing import List, Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist
@@ -294,8 +293,6 @@ class ShardedGaussianRasterizer(nn.Module):
 def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
     """One frame of the 2 M-Gaussian scene split over `world` GPUs (strong scaling): forward + backward with the
     collectives inside the timed region, device-timed, max over ranks."""
-    import json
-    from pathlib import Path
     sc = sc_cpu.to(dev)
     H, W = sc.height, sc.width
     g = torch.Generator().manual_seed(123)

@@ -14,7 +14,6 @@ leaves autograd reaches through the reference's getters.  There is no CPU path.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import List, NamedTuple, Optional, Sequence
 
 import numpy as np
