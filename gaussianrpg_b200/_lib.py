@@ -132,6 +132,7 @@ SYMBOLS = {
     "grpg_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int, _fp, _fp]),
     "grpg_stats_workspace_bytes": (C.c_size_t, [C.c_int]),
     "grpg_densify_stats": (C.c_int, [C.POINTER(StatsSubmodel), C.c_int, _fp, _fp, _fp, _fp]),
+    "grpg_densify_stats_ex": (C.c_int, [C.POINTER(StatsSubmodel), C.c_int, _fp, _fp, _fp, C.c_int, _fp, _fp]),
     "grpg_compose_workspace_bytes": (C.c_size_t, [C.c_int]),
     "grpg_compose_forward": (C.c_int, [C.POINTER(ComposeSubmodel), C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "grpg_compose_backward": (C.c_int, [C.POINTER(ComposeSubmodel), C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp,

@@ -224,7 +224,7 @@ int grpg_forward_geometry(const grpg_forward_args* a, int* num_binned, int* num_
     unsigned long long* host = pinned_word();
     cudaMemcpyAsync(host, g + L.num_rendered, 16, cudaMemcpyDeviceToHost, stream);
     if (int rc = check_cuda("forward_geometry", true, stream)) return rc;
-    if (host[0] >= (1ull << 30) || host[1] >= (1ull << 31)) return fail("too many Gaussian/tile instances (>= 2^30)");
+    if (host[0] >= (1ull << 31) || host[1] >= (1ull << 31)) return fail("too many Gaussian/tile instances (>= 2^31, the range of the reference's int num_rendered)");
     *num_binned = (int)host[0];
     if (num_rendered) *num_rendered = (int)host[1];
     return 0;

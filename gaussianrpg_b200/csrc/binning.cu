@@ -20,7 +20,7 @@ namespace grpg {
 constexpr int SCAN_IPT = 8;
 constexpr int SCAN_TILE = 256 * SCAN_IPT;
 constexpr uint32_t EMIT_CHUNK = 1024;                      // instances emitted per warp
-constexpr uint32_t EMIT_MAX_CHUNKS = (1u << 30) / EMIT_CHUNK + 2;  // R < 2^30 is enforced by the API
+constexpr uint32_t EMIT_MAX_CHUNKS = (1u << 31) / EMIT_CHUNK + 2;  // R < 2^31 (the reference's int num_rendered) is enforced by the API
 constexpr unsigned long long SC_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long SC_FLAG_PREFIX = 2ull << 62;
 constexpr unsigned long long SC_FLAG_MASK = 3ull << 62;

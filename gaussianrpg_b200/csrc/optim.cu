@@ -6,7 +6,7 @@
 //
 // B200 design.  Both ops are single-pass streaming: Adam reads 16 B and writes 12 B per parameter element (1.3 GB per
 // iteration at 2 M Gaussians), so one launch walks ALL tensors of ALL sub-models: a CTA owns a 4096-element chunk of one
-// tensor (looked up from a descriptor table with one parallel count), every thread keeps four independent 16-byte
+// tensor (looked up from a descriptor table by binary search), every thread keeps four independent 16-byte
 // loads per array in flight, nothing is re-read.  torch's foreach path makes seven passes over the same bytes per
 // optimiser and the reference has nine optimisers.
 #include <cuda_runtime.h>
@@ -35,6 +35,20 @@ struct AdamDev {
 };
 static_assert(sizeof(AdamDev) % 8 == 0, "table rows are read as 8-byte words");
 
+// Row of a descriptor table that owns CTA `b`: the largest k with chunk_begin[k] <= b.  The column is monotone
+// (empty tensors repeat their successor's value, so the largest k is never an empty one), hence a binary search;
+// every thread runs the same ~10 broadcast loads.  (A __syncthreads_count over per-thread partial counts would
+// under-count once a thread holds two matching rows, i.e. for tables longer than the block.)
+template <typename Row>
+__device__ __forceinline__ int owner_row(const Row* __restrict__ tab, int n, int b) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tab[mid].chunk_begin <= b) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamDev& d) {
     m = __fmaf_rn(d.w1, g - m, m);                  // lerp_(g, 1 - beta1): m + w (g - m)
     v = v * d.beta2;                                // mul_(beta2)
@@ -45,9 +59,7 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
 
 __global__ void __launch_bounds__(ADAM_THREADS) adam_step_kernel(const AdamDev* __restrict__ tab, int n) {
     __shared__ AdamDev d;
-    int c = 0;
-    for (int k = threadIdx.x; k < n; k += ADAM_THREADS) c += tab[k].chunk_begin <= (int)blockIdx.x ? 1 : 0;
-    const int k = __syncthreads_count(c) - 1;  // counts every k with chunk_begin <= blockIdx (monotone column)
+    const int k = owner_row(tab, n, (int)blockIdx.x);
     {
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(tab + k);
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(&d);
@@ -113,23 +125,28 @@ static_assert(sizeof(StatsDev) % 8 == 0, "");
 
 __global__ void __launch_bounds__(STATS_THREADS) densify_stats_kernel(const StatsDev* __restrict__ tab, int n_sub,
                                                                       const int* __restrict__ radii,
-                                                                      const float* __restrict__ vgrad) {
+                                                                      const float* __restrict__ vgrad,
+                                                                      const unsigned char* __restrict__ filter,
+                                                                      int what) {
     __shared__ StatsDev d;
-    int c = 0;
-    for (int k = threadIdx.x; k < n_sub; k += STATS_THREADS) c += tab[k].chunk_begin <= (int)blockIdx.x ? 1 : 0;
-    const int k = __syncthreads_count(c) - 1;
+    const int k = owner_row(tab, n_sub, (int)blockIdx.x);
     if (threadIdx.x == 0) d = tab[k];
     __syncthreads();
     const int j = ((int)blockIdx.x - d.chunk_begin) * STATS_THREADS + threadIdx.x;  // row inside the sub-model
     if (j >= d.n) return;
     const size_t i = (size_t)d.offset + j;                                           // row of the composed arrays
-    const int r = __ldcs(radii + i);
-    if (r <= 0) return;                                                              // visibility_filter = radii > 0
-    const float gx = __ldcs(vgrad + 3 * i), gy = __ldcs(vgrad + 3 * i + 1), gz = __ldcs(vgrad + 3 * i + 2);
-    d.max_radii[j] = fmaxf(d.max_radii[j], (float)r);       // street_gaussian_model.py:564-565 (radii.float())
-    d.accum[2 * j] += sqrtf(gx * gx + gy * gy);             // :576  torch.norm(grad[:, :2], dim=-1)
-    d.accum[2 * j + 1] += fabsf(gz);                        // :577  torch.norm(grad[:, 2:], dim=-1)
-    d.denom[j] += 1.0f;                                     // :578
+    // visibility_filter: the caller's boolean mask when one is passed, else radii > 0 (what the reference renderer
+    // builds, street_gaussian_renderer.py:268)
+    const int r = (filter == nullptr || (what & GRPG_STATS_MAX_RADII)) ? __ldcs(radii + i) : 0;
+    if (filter != nullptr ? filter[i] == 0 : r <= 0) return;
+    if (what & GRPG_STATS_MAX_RADII)
+        d.max_radii[j] = fmaxf(d.max_radii[j], (float)r);   // street_gaussian_model.py:564-565 (radii.float())
+    if (what & GRPG_STATS_GRADIENTS) {
+        const float gx = __ldcs(vgrad + 3 * i), gy = __ldcs(vgrad + 3 * i + 1), gz = __ldcs(vgrad + 3 * i + 2);
+        d.accum[2 * j] += sqrtf(gx * gx + gy * gy);         // :576  torch.norm(grad[:, :2], dim=-1)
+        d.accum[2 * j + 1] += fabsf(gz);                    // :577  torch.norm(grad[:, 2:], dim=-1)
+        d.denom[j] += 1.0f;                                 // :578
+    }
 }
 
 static int check_launch(const char* what) {
@@ -183,8 +200,16 @@ extern "C" size_t grpg_stats_workspace_bytes(int n_sub) {
 
 extern "C" int grpg_densify_stats(const grpg_stats_submodel* subs, int n_sub, const int* radii, const float* viewspace_grad,
                                   void* workspace, void* stream_) {
+    return grpg_densify_stats_ex(subs, n_sub, radii, viewspace_grad, nullptr, GRPG_STATS_MAX_RADII | GRPG_STATS_GRADIENTS,
+                                 workspace, stream_);
+}
+
+extern "C" int grpg_densify_stats_ex(const grpg_stats_submodel* subs, int n_sub, const int* radii,
+                                     const float* viewspace_grad, const unsigned char* visibility_filter, int what,
+                                     void* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_sub == 0) return 0;
+    if ((what & ~(GRPG_STATS_MAX_RADII | GRPG_STATS_GRADIENTS)) || what == 0) return grpg_loss_fail("grpg_densify_stats_ex: bad `what` mask");
     if (!subs || n_sub < 0 || n_sub > STATS_MAX_SUB) return grpg_loss_fail("grpg_densify_stats: 1..1024 sub-models per call");
     std::vector<StatsDev> tab(n_sub);
     long long offset = 0, chunks = 0;
@@ -200,11 +225,13 @@ extern "C" int grpg_densify_stats(const grpg_stats_submodel* subs, int n_sub, co
         chunks += (s.n + STATS_THREADS - 1) / STATS_THREADS;
     }
     if (chunks == 0) return 0;
-    if (!radii || !viewspace_grad || !workspace) return grpg_loss_fail("grpg_densify_stats: null input or workspace");
+    if (!workspace || ((what & GRPG_STATS_GRADIENTS) && !viewspace_grad) ||
+        (((what & GRPG_STATS_MAX_RADII) || !visibility_filter) && !radii))
+        return grpg_loss_fail("grpg_densify_stats: null input or workspace");
     if (cudaMemcpyAsync(workspace, tab.data(), tab.size() * sizeof(StatsDev), cudaMemcpyHostToDevice, stream) != cudaSuccess)
         return check_launch("grpg_densify_stats: table upload");
     ProfScope ps("densify_stats", stream);
     densify_stats_kernel<<<(unsigned)chunks, STATS_THREADS, 0, stream>>>(reinterpret_cast<const StatsDev*>(workspace), n_sub,
-                                                                        radii, viewspace_grad);
+                                                                        radii, viewspace_grad, visibility_filter, what);
     return check_launch("grpg_densify_stats");
 }

@@ -252,7 +252,9 @@ __global__ void __launch_bounds__(256, MINB) preprocess_bwd_kernel(
 
         // ---- cov3D -> scale / rotation (backward.cu:278-341) ----
         if (scales != nullptr) {
-            const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+            float4 q;  // 16-byte load when aligned, scalar loads for an offset contiguous view
+            if ((reinterpret_cast<uintptr_t>(rotations) & 15u) == 0) q = reinterpret_cast<const float4*>(rotations)[idx];
+            else q = make_float4(rotations[4 * (size_t)idx], rotations[4 * (size_t)idx + 1], rotations[4 * (size_t)idx + 2], rotations[4 * (size_t)idx + 3]);
             const float r = q.x, x = q.y, y = q.z, z = q.w;
             // Rm[c][r] as the glm matrix in the forward
             const float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},

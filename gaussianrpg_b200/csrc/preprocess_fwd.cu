@@ -48,6 +48,14 @@ __device__ __forceinline__ void cov3d_from_scale_rot(const float sx_in, const fl
     cov3D[5] = dot3(M20, M20, M21, M21, M22, M22);
 }
 
+// Quaternion of Gaussian idx: one 16-byte load when the array is 16-byte aligned, four scalar loads for a contiguous
+// view whose storage offset is not a multiple of four floats (the reference has no alignment requirement).
+__device__ __forceinline__ float4 load_quat(const float* __restrict__ rotations, size_t idx) {
+    if ((reinterpret_cast<uintptr_t>(rotations) & 15u) == 0) return reinterpret_cast<const float4*>(rotations)[idx];
+    const float* q = rotations + 4 * idx;
+    return make_float4(q[0], q[1], q[2], q[3]);
+}
+
 // Everything that determines visibility, keys and the 2D footprint of one Gaussian.
 __device__ __forceinline__ void project_gaussian(float x, float y, float z, const float* __restrict__ v,
                                                  const float* __restrict__ m, const float* cov3D, int W, int H,
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
 #pragma unroll
             for (int k = 0; k < 6; ++k) cov3D[k] = cov3D_precomp[6 * (size_t)idx + k];
         } else {
-            const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+            const float4 q = load_quat(rotations, (size_t)idx);
             const float* sc = stage_scales ? s_scales + 3 * threadIdx.x : scales + 3 * (size_t)idx;
             cov3d_from_scale_rot(sc[0], sc[1], sc[2], scale_modifier, q.x, q.y, q.z, q.w, cov3D);
             if (!forward_only) {
@@ -420,7 +428,7 @@ __global__ void __launch_bounds__(256) visible_filter_kernel(
 #pragma unroll
         for (int k = 0; k < 6; ++k) cov3D[k] = cov3D_precomp[6 * (size_t)idx + k];
     } else {
-        const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+        const float4 q = load_quat(rotations, (size_t)idx);
         cov3d_from_scale_rot(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2], scale_modifier, q.x, q.y, q.z,
                              q.w, cov3D);
     }

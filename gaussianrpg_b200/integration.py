@@ -13,7 +13,8 @@ drop-in.  The scene-graph compose and the optimiser plumbing live *inside* the r
   served from ONE fused `compose_scene` call per `parse_camera` (computed lazily on the first getter access);
 * `update_optimizer` (:536-553) steps every sub-model's Adam in one launch (`fused_adam_step`), then lets the
   non-Gaussian optimisers (actor pose, sky cube map, colour / pose correction) step as before;
-* `set_max_radii2D` + `add_densification_stats` (:555-578) become one launch.
+* `set_max_radii2D` and `add_densification_stats` (:555-578) become one launch each over all sub-models (instead of
+  four masked read-modify-writes per sub-model), with the caller's visibility mask.
 
 Everything the reference computes in `parse_camera` is reused as is: the per-actor pose is read back out of the
 expanded `self.obj_rots / self.obj_trans` rows (one row per actor, autograd intact), the flip mask out of
@@ -92,6 +93,7 @@ def install(cls, compose: Optional[Callable] = None, idft_base: Optional[Callabl
         opts = [getattr(self, n).optimizer for n in self.model_name_id.keys()
                 if not any(n.startswith(e) for e in exclude_list)]
         adam_step(opts)
+        self._grpg_composed = None  # the parameters changed in place: the cached compose is stale
         for o in opts:
             o.zero_grad(set_to_none=True)
         for extra in ("actor_pose", "sky_cubemap", "color_correction", "pose_correction"):
@@ -99,17 +101,36 @@ def install(cls, compose: Optional[Callable] = None, idft_base: Optional[Callabl
             if m is not None:
                 m.update_optimizer()
 
+    def _stats(self):
+        return [DensifyStats(m.max_radii2D, m.xyz_gradient_accum, m.denom)
+                for m in (getattr(self, n) for n in self.graph_gaussian_range.keys())]
+
+    # The reference's two calls keep their own semantics -- each applies its update immediately, with the mask the
+    # caller passes (street_gaussian_model.py:555-578) -- as one launch each over all sub-models.
     def set_max_radii2D(self, radii, visibility_filter):
-        self._grpg_radii = radii  # the statistics kernel derives the filter (radii > 0) itself; see add_densification_stats
+        stats_update(_stats(self), radii, None, visibility_filter, 1)
 
     def add_densification_stats(self, viewspace_point_tensor, visibility_filter):
-        radii = getattr(self, "_grpg_radii", None)
-        if radii is None:  # called without set_max_radii2D: the reference's behaviour
-            return orig["add_densification_stats"](self, viewspace_point_tensor, visibility_filter)
-        self._grpg_radii = None
-        models = [getattr(self, n) for n in self.graph_gaussian_range.keys()]
-        stats_update([DensifyStats(m.max_radii2D, m.xyz_gradient_accum, m.denom) for m in models], radii,
-                     viewspace_point_tensor.grad)
+        stats_update(_stats(self), None, viewspace_point_tensor.grad, visibility_filter, 2)
+
+    # anything that replaces or rewrites parameter tensors (densification, opacity reset) or changes which sub-models
+    # are composed invalidates the per-camera cache
+    def invalidating(name):
+        fn = cls.__dict__[name]
+
+        def wrapped(self, *a, **kw):
+            self._grpg_composed = None
+            try:
+                return fn(self, *a, **kw)
+            finally:
+                self._grpg_composed = None
+        wrapped.__name__ = name
+        return wrapped
+
+    for name in ("densify_and_prune", "reset_opacity", "set_visibility"):
+        if name in cls.__dict__ and callable(cls.__dict__[name]):
+            orig[name] = cls.__dict__[name]
+            setattr(cls, name, invalidating(name))
 
     cls.parse_camera = parse_camera
     cls.get_xyz = getter("xyz", "get_xyz")

@@ -15,7 +15,7 @@ There is no CPU path.
 """
 from __future__ import annotations
 
-from typing import NamedTuple, Sequence
+from typing import NamedTuple, Optional, Sequence
 
 import torch
 
@@ -103,22 +103,43 @@ class DensifyStats(NamedTuple):
     denom: torch.Tensor                # [n,1]
 
 
-def update_densification_stats(stats: Sequence[DensifyStats], radii: torch.Tensor,
-                               viewspace_point_tensor_grad: torch.Tensor) -> None:
-    """`StreetGaussianModel.set_max_radii2D(radii, radii > 0)` followed by
-    `add_densification_stats(viewspace_point_tensor, radii > 0)` (street_gaussian_model.py:555-578) for the
-    sub-models of `graph_gaussian_range` in order, in place, in one launch.  `radii` [P] (int32, the rasterizer's
-    output), `viewspace_point_tensor_grad` [P,3]; P = total rows of the listed sub-models.  The visibility filter is
-    `radii > 0`, which is what the reference renderer passes (street_gaussian_renderer.py:268)."""
-    _require_cuda(radii, "radii")
+STATS_MAX_RADII, STATS_GRADIENTS = 1, 2  # GRPG_STATS_* (include/grpg_optim.h)
+
+
+def update_densification_stats(stats: Sequence[DensifyStats], radii: Optional[torch.Tensor],
+                               viewspace_point_tensor_grad: Optional[torch.Tensor],
+                               visibility_filter: Optional[torch.Tensor] = None,
+                               what: int = STATS_MAX_RADII | STATS_GRADIENTS) -> None:
+    """`StreetGaussianModel.set_max_radii2D(radii, visibility_filter)` (what & STATS_MAX_RADII) and/or
+    `add_densification_stats(viewspace_point_tensor, visibility_filter)` (what & STATS_GRADIENTS)
+    (street_gaussian_model.py:555-578) for the sub-models of `graph_gaussian_range` in order, in place, in one launch.
+    `radii` [P] (int32, the rasterizer's output), `viewspace_point_tensor_grad` [P,3]; P = total rows of the listed
+    sub-models.  `visibility_filter` [P] bool: the mask the caller passes to the reference's methods; None means
+    `radii > 0`, which is what the reference renderer builds (street_gaussian_renderer.py:268)."""
+    ref_t = radii if radii is not None else visibility_filter
+    if ref_t is None:
+        raise RuntimeError("update_densification_stats: radii or visibility_filter is required")
+    _require_cuda(ref_t, "radii / visibility_filter")
     lib = _lib.load()
-    dev = radii.device
-    P = int(radii.shape[0])
-    if sum(int(s.denom.shape[0]) for s in stats) != P or tuple(viewspace_point_tensor_grad.shape) != (P, 3):
+    dev = ref_t.device
+    P = int(ref_t.shape[0])
+    if sum(int(s.denom.shape[0]) for s in stats) != P:
         raise RuntimeError("update_densification_stats: sub-model sizes must add up to len(radii); grad must be [P,3]")
-    r = radii if (radii.dtype == torch.int32 and radii.is_contiguous()) else radii.to(torch.int32).contiguous()
-    g = viewspace_point_tensor_grad
-    g = g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()
+    r = g = f = None
+    if radii is not None:
+        r = radii if (radii.dtype == torch.int32 and radii.is_contiguous()) else radii.to(torch.int32).contiguous()
+    elif what & STATS_MAX_RADII:
+        raise RuntimeError("update_densification_stats: radii is required for the max_radii2D update")
+    if what & STATS_GRADIENTS:
+        g = viewspace_point_tensor_grad
+        if g is None or tuple(g.shape) != (P, 3):
+            raise RuntimeError("update_densification_stats: sub-model sizes must add up to len(radii); grad must be [P,3]")
+        g = g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()
+    if visibility_filter is not None:
+        if tuple(visibility_filter.shape) != (P,) or visibility_filter.device != dev:
+            raise RuntimeError("update_densification_stats: visibility_filter must be [P] on the radii's device")
+        f = visibility_filter if visibility_filter.dtype in (torch.bool, torch.uint8) else visibility_filter != 0
+        f = f.contiguous()
     tab = (_lib.StatsSubmodel * len(stats))()
     for t, s in zip(tab, stats):
         n = int(s.denom.shape[0])
@@ -132,6 +153,7 @@ def update_densification_stats(stats: Sequence[DensifyStats], radii: torch.Tenso
         return
     ws = torch.empty(int(lib.grpg_stats_workspace_bytes(len(stats))), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        if lib.grpg_densify_stats(tab, len(stats), r.data_ptr(), g.data_ptr(), ws.data_ptr(),
-                                  _lib.current_stream_ptr(dev)) != 0:
+        if lib.grpg_densify_stats_ex(tab, len(stats), None if r is None else r.data_ptr(),
+                                     None if g is None else g.data_ptr(), None if f is None else f.data_ptr(), int(what),
+                                     ws.data_ptr(), _lib.current_stream_ptr(dev)) != 0:
             raise RuntimeError(_lib.last_error())

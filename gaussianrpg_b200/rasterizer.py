@@ -52,13 +52,15 @@ def _call_with_snapshot(fn, args, debug: bool, dump_name: str, what: str):
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, grad_mode=True):
         rs = raster_settings
         native_args = (rs.bg, means3D, colors_precomp, semantics, opacities, scales, rotations, rs.scale_modifier,
                        cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
                        rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
-        # when no input requires grad (eval / torch.no_grad) the backward-only state is not materialised
-        fwd_only = not any(ctx.needs_input_grad)
+        # When nothing can ask for a backward the backward-only state (cov3D, clamp flags) is not materialised.
+        # `needs_input_grad` mirrors the tensors' requires_grad flags whatever the grad mode, and grad mode is always
+        # off inside Function.forward, so the caller samples torch.is_grad_enabled() and passes it in (`grad_mode`).
+        fwd_only = (not grad_mode) or not any(ctx.needs_input_grad)
         (num_rendered, color, depth, alpha, semantic, radii, geom, binning, img) = _call_with_snapshot(
             lambda *a_: _C.rasterize_gaussians(*a_, _forward_only=fwd_only), native_args, rs.debug, "snapshot_fw.dump",
             "forward")
@@ -91,13 +93,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         # rotations, cov3Ds_precomp, raster_settings
         grads = (g_means3D, g_means2D, g_sh, g_colors, g_sem, g_opac, g_scales, g_rot, g_cov3D)
         # autograd rejects a gradient for an argument that was not a tensor (e.g. means2D=None in eval)
-        return tuple(g if is_t else None for g, is_t in zip(grads, ctx.tensor_inputs)) + (None,)
+        return tuple(g if is_t else None for g, is_t in zip(grads, ctx.tensor_inputs)) + (None, None)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                                     cov3Ds_precomp, raster_settings, torch.is_grad_enabled())
 
 
 def _empty() -> torch.Tensor:

@@ -108,7 +108,11 @@ class _ComposeScene(torch.autograd.Function):
                                           opa.data_ptr(), feat.data_ptr(), _lib.current_stream_ptr(dev))
         if rc != 0:
             raise RuntimeError(_lib.last_error())
-        ctx.meta, ctx.subs, ctx.pose, ctx.desc = meta, subs, pose, desc
+        # Parameters and pose go through save_for_backward so that autograd's version counters catch an in-place
+        # update (optimiser step, reset_opacity) between this forward and its backward, which recomputes from them.
+        ctx.meta = meta
+        ctx.has_pose = tuple(p is not None for p in pose)
+        ctx.save_for_backward(*[t for s_ in subs for t in s_], *[p for p in pose if p is not None])
         ctx.pose_shapes = (None if obj_rots is None else obj_rots.shape, None if obj_trans is None else obj_trans.shape)
         ctx.param_shapes = [p.shape for p in params]
         return xyz, rot, scl, opa, feat
@@ -117,7 +121,10 @@ class _ComposeScene(torch.autograd.Function):
     def backward(ctx, g_xyz, g_rot, g_scl, g_opa, g_feat):
         lib = _lib.load()
         n_sub, is_actor, fourier, M, idft_h, flips = ctx.meta
-        subs = ctx.subs
+        saved = ctx.saved_tensors  # raises if a saved parameter was modified in place since the forward
+        subs = [tuple(saved[_N_PARAMS * k:_N_PARAMS * (k + 1)]) for k in range(n_sub)]
+        rest = list(saved[_N_PARAMS * n_sub:])
+        pose = tuple(rest.pop(0) if has else None for has in ctx.has_pose)
         dev = subs[0][0].device
         P = sum(int(s[0].shape[0]) for s in subs)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -131,12 +138,7 @@ class _ComposeScene(torch.autograd.Function):
         views = [g for gs in grads for g in gs]
         d_rots, d_trans = torch.empty((n_sub, 4), **f32), torch.empty((n_sub, 3), **f32)
         ws = torch.empty(max(int(lib.grpg_compose_workspace_bytes(n_sub)), 256), dtype=torch.uint8, device=dev)
-        desc = ctx.desc  # the forward's table (it holds this call's parameter pointers); add the gradient pointers
-        for k, g in enumerate(grads):
-            if g[0].numel():
-                d = desc[k]
-                d.d_xyz, d.d_scaling, d.d_rotation, d.d_opacity, d.d_features_dc = (t.data_ptr() for t in g[:5])
-                d.d_features_rest = g[5].data_ptr() if g[5].numel() else None
+        desc = _descriptors(subs, is_actor, fourier, pose, idft_h, flips, grads)
         with torch.cuda.device(dev):
             rc = lib.grpg_compose_backward(desc, n_sub, M, ws.data_ptr(), g_xyz.data_ptr(), g_rot.data_ptr(),
                                            g_scl.data_ptr(), g_opa.data_ptr(), g_feat.data_ptr(), d_rots.data_ptr(),

@@ -60,6 +60,18 @@ size_t grpg_stats_workspace_bytes(int n_sub);
 int grpg_densify_stats(const grpg_stats_submodel* subs, int n_sub, const int* radii, const float* viewspace_grad,
                        void* workspace, void* stream);
 
+
+/* The two halves on their own and with the caller's mask, for callers that keep the reference's two-call protocol
+ * (`set_max_radii2D(radii, visibility_filter)` then `add_densification_stats(viewspace_point_tensor,
+ * visibility_filter)`, street_gaussian_model.py:555-578) or pass a filter other than radii > 0:
+ * `what` = GRPG_STATS_MAX_RADII and/or GRPG_STATS_GRADIENTS; `visibility_filter` [P] bytes (0 / non-zero, a torch
+ * bool tensor) or NULL for radii > 0.  `radii` may be NULL when only GRPG_STATS_GRADIENTS is asked for with a filter,
+ * `viewspace_grad` when only GRPG_STATS_MAX_RADII is. */
+#define GRPG_STATS_MAX_RADII 1
+#define GRPG_STATS_GRADIENTS 2
+int grpg_densify_stats_ex(const grpg_stats_submodel* subs, int n_sub, const int* radii, const float* viewspace_grad,
+                          const unsigned char* visibility_filter, int what, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

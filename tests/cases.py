@@ -126,3 +126,22 @@ def rel_err(a: np.ndarray, b: np.ndarray) -> float:
         return 0.0
     den = float(np.abs(b).max())
     return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max()) / (den + 1e-30)
+
+
+def row_err(a: np.ndarray, b: np.ndarray, floor_frac: float = 1e-6) -> np.ndarray:
+    """Per-Gaussian relative error (the per-element check with an absolute floor of SURVEY 8(d)): for every row i,
+    max_j |a_ij - b_ij| / (max_j |b_ij| + floor) with floor = floor_frac * max |b|.  Unlike `rel_err` it does not let
+    the few large-gradient Gaussians hide errors on the many small-gradient ones (far Gaussians, dL_drotations):
+    every row whose gradient is more than a millionth of the tensor's largest is checked against its own scale."""
+    if a.size == 0:
+        return np.zeros(0)
+    a2 = a.reshape(a.shape[0], -1).astype(np.float64)
+    b2 = b.reshape(b.shape[0], -1).astype(np.float64)
+    floor = floor_frac * float(np.abs(b2).max()) + 1e-30
+    return np.abs(a2 - b2).max(axis=1) / (np.abs(b2).max(axis=1) + floor)
+
+
+def row_violations(a: np.ndarray, b: np.ndarray, tol: float = 1e-3) -> float:
+    """fraction of rows whose `row_err` exceeds tol"""
+    e = row_err(a, b)
+    return float((e > tol).mean()) if e.size else 0.0

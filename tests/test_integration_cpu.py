@@ -39,18 +39,25 @@ def patched():
         for o in opts:
             o.step()
 
-    def stats_update(stats, radii, grad):
-        from oracle import optim_oracle
+    def stats_update(stats, radii, grad, visibility_filter=None, what=3):
+        """CPU stand-in for optim.update_densification_stats (same signature and semantics)."""
         calls["stats"] += 1
-        out = optim_oracle.densify_stats(radii.numpy(), grad.numpy(), [dict(max_radii2D=s.max_radii2D.numpy(),
-                                         xyz_gradient_accum=s.xyz_gradient_accum.numpy(), denom=s.denom.numpy()) for s in stats])
-        for s, o in zip(stats, out):
-            s.max_radii2D.copy_(torch.from_numpy(o["max_radii2D"]))
-            s.xyz_gradient_accum.copy_(torch.from_numpy(o["xyz_gradient_accum"]))
-            s.denom.copy_(torch.from_numpy(o["denom"]))
+        off = 0
+        for s in stats:
+            n = s.denom.shape[0]
+            vis = (visibility_filter if visibility_filter is not None else radii > 0)[off:off + n].bool()
+            if what & 1:
+                s.max_radii2D[vis] = torch.max(s.max_radii2D[vis], radii[off:off + n].float()[vis])
+            if what & 2:
+                g = grad[off:off + n]
+                s.xyz_gradient_accum[vis, 0:1] += torch.norm(g[vis, :2], dim=-1, keepdim=True)
+                s.xyz_gradient_accum[vis, 1:2] += torch.norm(g[vis, 2:], dim=-1, keepdim=True)
+                s.denom[vis] += 1
+            off += n
 
     orig = integration.install(sgm.StreetGaussianModel, compose=_torch_compose, idft_base=compose_cases.idft_base,
                                adam_step=adam_step, stats_update=stats_update)
+    model._grpg_orig = orig
     try:
         yield sgm, model, case, want, obj_rots, obj_trans, calls
     finally:
@@ -123,8 +130,10 @@ def test_patched_optimizer_step_and_statistics(patched):
     vp = torch.zeros(sum(sizes), 3, requires_grad=True)
     vp.grad = grad.clone()
     model.set_max_radii2D(radii, radii > 0)
+    # like the reference, each call takes effect immediately (set_max_radii2D alone must already update max_radii2D)
+    assert any(float(getattr(model, n).max_radii2D.max()) > 0 for n in names)
     model.add_densification_stats(vp, radii > 0)
-    assert calls["stats"] == 1
+    assert calls["stats"] == 2  # one launch per call, over all sub-models
     got = [(getattr(model, n).max_radii2D.clone(), getattr(model, n).xyz_gradient_accum.clone(), getattr(model, n).denom.clone())
            for n in names]
     # expected: the oracle, which tests/test_optim_oracle_cpu.py pins to the reference's own two methods
@@ -135,3 +144,17 @@ def test_patched_optimizer_step_and_statistics(patched):
     for (mr, acc, den), w in zip(got, want_stats):
         assert np.array_equal(mr.numpy(), w["max_radii2D"]) and np.array_equal(den.numpy(), w["denom"])
         assert np.allclose(acc.numpy(), w["xyz_gradient_accum"], rtol=1e-6)
+    # a caller's own mask (not radii > 0) is honoured: patched pair == the reference's original pair on a copy
+    mask = (radii > 0) & (torch.arange(radii.shape[0]) % 3 != 0)
+    snap = [(m.max_radii2D.clone(), m.xyz_gradient_accum.clone(), m.denom.clone()) for m in (getattr(model, n) for n in names)]
+    model.set_max_radii2D(radii * 2, mask)
+    model.add_densification_stats(vp, mask)
+    patched_out = [(m.max_radii2D.clone(), m.xyz_gradient_accum.clone(), m.denom.clone()) for m in (getattr(model, n) for n in names)]
+    for n, (a, b, c) in zip(names, snap):
+        m = getattr(model, n)
+        m.max_radii2D, m.xyz_gradient_accum, m.denom = a, b, c
+    model._grpg_orig["set_max_radii2D"](model, radii * 2, mask)
+    model._grpg_orig["add_densification_stats"](model, vp, mask)
+    for n, (a, b, c) in zip(names, patched_out):
+        m = getattr(model, n)
+        assert torch.equal(m.max_radii2D, a) and torch.equal(m.denom, c) and torch.allclose(m.xyz_gradient_accum, b)

@@ -97,6 +97,58 @@ def test_fused_adam_many_optimizers_one_launch_vs_torch(cuda_device):
                 assert float(oa.state[a[k]]["step"]) == float(ob.state[b[k]]["step"])
 
 
+def test_more_tensors_than_threads_in_one_launch(cuda_device):
+    """Descriptor tables longer than the 256-thread block (a scene with background + > 36 actors has > 256 tensors,
+    7 per sub-model): 45 sub-models x 7 tensors = 315 rows in ONE launch against stock torch.optim.Adam, and the
+    statistics over 300 sub-models against the reference's masked formulation."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(9)
+    n_sub = 45
+    ours, theirs, pa, pb = [], [], [], []
+    for i in range(n_sub):
+        n = 97 + 131 * i  # ragged: chunks end inside and across the 4096-element tiles
+        case = dict(n=n, M=4, F=3, scale=1.0)
+        shapes = dict(optim_cases.SHAPES(n, 4, 3))
+        shapes["semantic"] = (n, 2)  # non-empty, so that all 7 tensors of a sub-model are listed
+        base = {k: torch.randn(*s, generator=g) for k, s in shapes.items()}
+        a = {k: torch.nn.Parameter(v.to(dev)) for k, v in base.items()}
+        b = {k: torch.nn.Parameter(v.to(dev).clone()) for k, v in base.items()}
+        pa.append(a); pb.append(b)
+        ours.append(_training_setup(a, case))
+        theirs.append(torch.optim.Adam([dict(lr=grp["lr"], name=grp["name"],
+                                             params=[b[k] for k in optim_cases.PARAMS if NAMES[k] == grp["name"]])
+                                        for grp in ours[-1].param_groups], lr=0.0, eps=1e-15))
+    for it in range(2):
+        for a, b in zip(pa, pb):
+            for k in optim_cases.PARAMS:
+                gr = (torch.randn(a[k].shape, generator=g) * 1e-2).to(dev)
+                a[k].grad, b[k].grad = gr, gr.clone()
+        assert optim.fused_adam_step(ours) == n_sub * 7 > 256
+        for o in theirs:
+            o.step()
+    for a, b in zip(pa, pb):
+        for k in optim_cases.PARAMS:
+            assert _rel(a[k], b[k].detach().cpu().numpy()) <= 1e-6, k
+
+    sizes = [5 + (37 * i) % 700 for i in range(300)]
+    radii, grad, subs = optim_cases.stats_inputs(sizes, seed=4)
+    radii, grad = radii.to(dev), grad.to(dev)
+    stats = [optim.DensifyStats(*(s[k].to(dev) for k in ("max_radii2D", "xyz_gradient_accum", "denom"))) for s in subs]
+    want = [{k: s[k].to(dev).clone() for k in s} for s in subs]
+    optim.update_densification_stats(stats, radii, grad)
+    off, vis_all, rf = 0, radii > 0, radii.float()
+    for w, n in zip(want, sizes):
+        vis, gg = vis_all[off:off + n], grad[off:off + n]
+        w["max_radii2D"][vis] = torch.max(w["max_radii2D"][vis], rf[off:off + n][vis])
+        w["xyz_gradient_accum"][vis, 0:1] += torch.norm(gg[vis, :2], dim=-1, keepdim=True)
+        w["xyz_gradient_accum"][vis, 1:2] += torch.norm(gg[vis, 2:], dim=-1, keepdim=True)
+        w["denom"][vis] += 1
+        off += n
+    for s, w in zip(stats, want):
+        assert torch.equal(s.max_radii2D, w["max_radii2D"]) and torch.equal(s.denom, w["denom"])
+        assert torch.allclose(s.xyz_gradient_accum, w["xyz_gradient_accum"], rtol=3e-7, atol=0)
+
+
 def test_densification_surgery_on_fused_adam_state(cuda_device):
     """The reference's optimiser-state surgery (gaussian_model.py:394-470) works on FusedAdam: prune then append."""
     case = dict(n=100, M=4, F=1, scale=1.0)

@@ -114,24 +114,38 @@ def test_non_default_stream_and_noncontiguous_inputs(cuda_device):
 
 
 def test_misaligned_views_take_the_plain_load_path(cuda_device):
-    """preprocess stages 16-byte-aligned attribute slices with TMA bulk copies; a contiguous view that starts
-    4 bytes into its storage must give the same answer through the fallback loads."""
+    """preprocess stages 16-byte-aligned attribute slices with TMA bulk copies and reads quaternions as float4; a
+    contiguous view that starts 4 bytes into its storage (every per-Gaussian input, rotations included) must give the
+    same images, gradients and visible_filter results through the fallback loads."""
     sc = _scene(cuda_device, P=1500, W=96, H=64)
-    base = GaussianRasterizer(sc.settings())(means2D=None, **sc.raster_kwargs())
-    kw = sc.raster_kwargs()
 
     def shifted(t):
         buf = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
-        buf[1:] = t.reshape(-1)
+        buf[1:] = t.detach().reshape(-1)
         v = buf[1:].view(t.shape)
         assert v.data_ptr() % 16 != 0 and v.is_contiguous()
         return v
 
-    for k in ("means3D", "scales", "shs"):
-        kw[k] = shifted(kw[k])
-    other = GaussianRasterizer(sc.settings())(means2D=None, **kw)
+    def run(shift):
+        kw = {}
+        for k, v in sc.raster_kwargs().items():
+            if torch.is_tensor(v) and k in ("means3D", "scales", "shs", "rotations", "opacities"):
+                v = (shifted(v) if shift else v.detach().clone()).requires_grad_(True)
+            kw[k] = v
+        out = GaussianRasterizer(sc.settings())(means2D=None, **kw)
+        (out[0].sum() + 0.1 * out[2].sum() + out[3].sum()).backward()
+        return out, {k: v.grad for k, v in kw.items() if torch.is_tensor(v) and v.requires_grad}
+
+    base, gbase = run(False)
+    other, gother = run(True)
     for a, b in zip(base, other):
         assert torch.equal(a, b)
+    assert set(gbase) == set(gother) and len(gbase) == 5
+    for k in gbase:  # same kernels, same inputs: only the atomic order of the blend backward differs
+        assert float((gbase[k] - gother[k]).abs().max()) <= 1e-3 * float(gbase[k].abs().max()), k
+    r0, m0 = GaussianRasterizer(sc.settings()).visible_filter(sc.means3D, sc.scales, sc.rotations)
+    r1, m1 = GaussianRasterizer(sc.settings()).visible_filter(shifted(sc.means3D), shifted(sc.scales), shifted(sc.rotations))
+    assert torch.equal(r0, r1) and torch.equal(m0, m1)
 
 
 def test_binning_workspace_guess_too_small_and_too_large(cuda_device):
