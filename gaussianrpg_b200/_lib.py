@@ -122,6 +122,7 @@ SYMBOLS = {
     "grpg_visible_filter": (C.c_int, [C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_float, _fp, _fp, _fp, _fp,
                                       C.c_float, C.c_float, _fp, _fp, _fp]),
     "grpg_debug_reference_keys": (C.c_int, [C.c_int, C.c_longlong, _fp, _fp, _fp, _fp]),
+    "grpg_debug_packed_math_check": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, _fp, _fp]),
     "grpg_profile_begin": (C.c_int, []),
     "grpg_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
     "grpg_last_error": (C.c_char_p, []),

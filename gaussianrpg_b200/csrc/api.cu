@@ -27,6 +27,8 @@ void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tile
                           uint32_t* point_list, void* scratch, uint2* ranges, int num_sms, cudaStream_t stream);
 void launch_reference_keys(long long R, const uint32_t* point_list, const uint32_t* tile_keys, const Rec* rec,
                            unsigned long long* keys, cudaStream_t stream);
+void launch_packed_math_check(uint32_t first_bits, uint32_t last_bits, int negative, unsigned long long* out,
+                              cudaStream_t stream);
 // blend_fwd.cu / blend_bwd.cu / preprocess_bwd.cu
 void launch_blend_fwd(const grpg_forward_args* a, const uint2* ranges, const uint32_t* point_list, const Rec* rec,
                       uint32_t* n_contrib, cudaStream_t stream);
@@ -343,6 +345,13 @@ int grpg_debug_reference_keys(int P, long long R, const void* geom_ws, const voi
     launch_reference_keys(R, (const uint32_t*)(b + BL.point_list), (const uint32_t*)(b + BL.tile_keys),
                           (const Rec*)(g + L.rec), (unsigned long long*)keys_out, (cudaStream_t)stream);
     return check_cuda("reference_keys", false, (cudaStream_t)stream);
+}
+
+int grpg_debug_packed_math_check(uint32_t first_bits, uint32_t last_bits, int negative, unsigned long long* out,
+                                 void* stream) {
+    if (!out || last_bits < first_bits) return fail("grpg_debug_packed_math_check: bad arguments");
+    launch_packed_math_check(first_bits, last_bits, negative, out, (cudaStream_t)stream);
+    return check_cuda("packed_math_check", false, (cudaStream_t)stream);
 }
 
 }  // extern "C"

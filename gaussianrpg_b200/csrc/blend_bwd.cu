@@ -17,7 +17,7 @@ namespace grpg {
 
 constexpr int BWD_BATCH = 256;
 constexpr int GREC = 12;  // floats per Gaussian in the gradient record
-#define GRPG_BWD_PPL_DEFAULT 2  // measured on the 2 M scene: 1 -> 1.21 ms, 2 -> 1.08 ms, 4 -> 1.20 ms
+#define GRPG_BWD_PPL_DEFAULT 3  // 3 = the packed two-pixel kernel; measured on the 2 M scene: 1 -> 1.21 ms, 2 -> 1.08 ms, 4 -> 1.20 ms
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -440,13 +440,244 @@ __global__ void __launch_bounds__(256 / PPL, MINB) blend_bwd_wide_kernel(
     cp_async_wait_all();
 }
 
+// Same butterfly as warp_reduce12 with the additions of each level issued as packed FADD2 (13 -> 8 add instructions).
+__device__ __forceinline__ float warp_reduce12_packed(const float (&v)[12], int lane) {
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+    float k[6], r[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float send = h4 ? v[i] : v[i + 6];
+        k[i] = h4 ? v[i + 6] : v[i];
+        r[i] = __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const float2 a01 = fadd2(f2(k[0], k[1]), f2(r[0], r[1]));
+    const float2 a23 = fadd2(f2(k[2], k[3]), f2(r[2], r[3]));
+    const float2 a45 = fadd2(f2(k[4], k[5]), f2(r[4], r[5]));
+    const float a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+    float kb[3], rb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float send = h3 ? a[i] : a[i + 3];
+        kb[i] = h3 ? a[i + 3] : a[i];
+        rb[i] = __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float2 b01 = fadd2(f2(kb[0], kb[1]), f2(rb[0], rb[1]));
+    const float b2 = kb[2] + rb[2];
+    const float s0 = __shfl_xor_sync(0xffffffffu, h2 ? b01.x : b2, 4);
+    const float s1 = __shfl_xor_sync(0xffffffffu, h2 ? b01.y : 0.f, 4);
+    const float2 c = fadd2(f2(h2 ? b2 : b01.x, h2 ? 0.f : b01.y), f2(s0, s1));
+    float q = (h1 ? c.y : c.x) + __shfl_xor_sync(0xffffffffu, h1 ? c.x : c.y, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    return q;
+}
+
+// ---- packed variant (no semantic channels): two vertically adjacent pixels per lane, FADD2 / FMUL2 / FFMA2 ------------
+// Pixel layout and masking as in blend_fwd_packed_kernel: lane l owns (l & 7, 2 (l >> 3)) and the pixel below it, and the
+// whole per-pixel chain -- `power`, expf, alpha, T / (1 - alpha), the collapsed recurrence, the 2D-mean / conic /
+// opacity / colour / depth partials -- is issued once per lane on float2 operands.  A pixel that does not take part
+// (behind its last contributor, power > 0, alpha < 1/255) runs with alpha = 0 and G = 0: rcp(1 - 0) = 1 leaves T, the
+// recurrence keeps A (fma(0, s, 1 * A) = A) and every partial it adds is an exact zero.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) blend_bwd_packed_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const Rec* __restrict__ rec, int W, int H,
+    const float* __restrict__ bg_color, const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
+    const float* __restrict__ dL_dalphas, float* __restrict__ grad_rec /*[P][12]*/, int HL, int row_stride,
+    int row_phase, int grads_full) {
+    constexpr int NT = 128, NW = 4, RPT = BWD_BATCH / NT;
+    __shared__ __align__(16) float4 s_rec2[2][BWD_BATCH * 3];
+    __shared__ uint32_t s_id2[2][BWD_BATCH];
+    __shared__ int s_maxlast[NW];
+    __shared__ uint16_t s_q[NW][BWD_BATCH];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
+    const uint32_t tile = blockIdx.y * tiles_x + blockIdx.x;
+    const int bx0 = blockIdx.x * GRPG_TILE + (warp & 1) * 8;
+    const int wy0 = (warp >> 1) * 8;
+    const int by0 = (blockIdx.y * row_stride + row_phase) * GRPG_TILE + wy0;
+    const int pix_x = bx0 + (lane & 7);
+    const int row0 = by0 + 2 * (lane >> 3);
+    const float pxf = (float)pix_x;
+    const float2 npy = f2(-(float)row0, -(float)(row0 + 1));
+    const float bx_lo = (float)bx0, bx_hi = (float)(bx0 + 7), by_lo = (float)by0, by_hi = (float)(by0 + 7);
+    const size_t hw = grads_full ? (size_t)H * W : (size_t)HL * W;
+
+    const uint2 range = ranges[tile];
+    const int n_inst = (int)(range.y - range.x);
+    const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
+
+    float sT[2], sL[2], sd0[2], sd1[2], sd2[2], sdd[2], sda[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int pix_y = row0 + p;
+        const int loc_y = blockIdx.y * GRPG_TILE + wy0 + 2 * (lane >> 3) + p;
+        const bool inside = pix_x < W && pix_y < H;
+        const size_t pid = (size_t)loc_y * W + pix_x;
+        const size_t gpx = grads_full ? (size_t)pix_y * W + pix_x : pid;
+        sT[p] = inside ? 1.0f - alphas[pid] : 0.0f;  // T_final (backward.cu:468)
+        sL[p] = inside ? __uint_as_float(n_contrib[pid]) : 0.0f;
+        sd0[p] = inside ? dL_dpixels[gpx] : 0.f;
+        sd1[p] = inside ? dL_dpixels[hw + gpx] : 0.f;
+        sd2[p] = inside ? dL_dpixels[2 * hw + gpx] : 0.f;
+        sdd[p] = inside ? dL_dpixel_depths[gpx] : 0.f;
+        sda[p] = inside ? dL_dalphas[gpx] : 0.f;
+    }
+    float2 T = f2(sT[0], sT[1]);
+    const float2 dp0 = f2(sd0[0], sd0[1]), dp1 = f2(sd1[0], sd1[1]), dp2 = f2(sd2[0], sd2[1]);
+    const float2 dpd = f2(sdd[0], sdd[1]), dpa = f2(sda[0], sda[1]);
+    // -(T_final * (bg . dL_dpixel)): the background term of dL/dalpha, multiplied by 1 / (1 - alpha) per Gaussian
+    const float2 ntfb = f2(-(sT[0] * (bg0 * sd0[0] + bg1 * sd1[0] + bg2 * sd2[0])),
+                           -(sT[1] * (bg0 * sd0[1] + bg1 * sd1[1] + bg2 * sd2[1])));
+    const int last0 = (int)__float_as_uint(sL[0]), last1 = (int)__float_as_uint(sL[1]);
+    float2 accA = f2(0.f);
+
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    const int red_sub = ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const int red_slot = red_sub < 3 ? ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + red_sub : 11;
+    const float slot_scale = red_slot == 0 ? -ddelx_dx : red_slot == 1 ? -ddely_dy : (red_slot >= 3 && red_slot <= 5) ? -0.5f : 1.0f;
+
+    const int wmax = __reduce_max_sync(0xffffffffu, max(last0, last1));
+    if (lane == 0) s_maxlast[warp] = wmax;
+    __syncthreads();
+    int tile_last = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) tile_last = max(tile_last, s_maxlast[w]);
+    tile_last = min(tile_last, n_inst);
+
+    auto stage = [&](int buf, int top, const uint32_t (&id)[RPT]) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int t = tid + r * NT;
+            if (top - 1 - t >= 0) {
+                const float4* src = reinterpret_cast<const float4*>(rec + id[r]);
+                float4* d = &s_rec2[buf][3 * t];
+                cp_async16(d, src); cp_async16(d + 1, src + 1); cp_async16(d + 2, src + 2);
+                s_id2[buf][t] = id[r];
+            }
+        }
+        cp_async_commit();
+    };
+    auto fetch_id = [&](int top, uint32_t (&id)[RPT]) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int t = tid + r * NT;
+            id[r] = top - 1 - t >= 0 ? point_list[range.x + top - 1 - t] : 0u;
+        }
+    };
+    uint32_t id_next[RPT];
+    fetch_id(tile_last, id_next);
+    stage(0, tile_last, id_next);
+    fetch_id(tile_last - BWD_BATCH, id_next);
+
+    for (int top = tile_last, it = 0; top > 0; top -= BWD_BATCH, ++it) {
+        const int cnt = min(BWD_BATCH, top);
+        cp_async_wait_all();
+        __syncthreads();
+        const float4* s_rec = s_rec2[it & 1];
+        const uint32_t* s_id = s_id2[it & 1];
+        stage((it + 1) & 1, top - BWD_BATCH, id_next);
+        fetch_id(top - 2 * BWD_BATCH, id_next);
+        if (wmax <= top - cnt) continue;
+
+        uint16_t* q = s_q[warp];
+        const char* rec_base = reinterpret_cast<const char*>(s_rec);
+        int n_q = 0;
+        for (int g0 = 0; g0 < cnt; g0 += 32) {
+            const int j = g0 + lane;
+            const bool hit = j < cnt && (top - 1 - j) < wmax &&
+                             footprint_hits_exact(s_rec[3 * j], s_rec[3 * j + 1], bx_lo, bx_hi, by_lo, by_hi);
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+            n_q += __popc(m);
+        }
+        __syncwarp();
+        for (int qi = 0; qi < n_q; ++qi) {
+            const int k = (int)q[qi];
+            const float4* rk = reinterpret_cast<const float4*>(rec_base + (uint32_t)k * 48u);
+            const int pos = top - 1 - k;
+            const float4 a = rk[0];
+            const float4 b = rk[1];
+            const uint32_t gid = s_id[k];
+            const float dx = fadd(-pxf, a.x);
+            const float2 dy = fadd2(f2(a.y), npy);
+            const float2 dxAB = fmul2(f2(dx), f2(b.x, b.y));
+            const float2 tc = fmul2(dy, fmul2(dy, f2(b.z)));
+            const float2 tb = fmul2(dy, f2(dxAB.y));
+            const float2 power = ffma2(ffma2(f2(dx), f2(dxAB.x), tc), f2(-0.5f), f2(-tb.x, -tb.y));
+            const bool mb0 = (pos < last0) && !(power.x > 0.0f) && !(power.x < a.w);
+            const bool mb1 = (pos < last1) && !(power.y > 0.0f) && !(power.y < a.w);
+            if (!__any_sync(0xffffffffu, mb0 || mb1)) continue;
+            const float2 G = expf2_exact(power);
+            float2 al = fmul2(f2(b.w), G);
+            al = f2(fminf(0.99f, al.x), fminf(0.99f, al.y));
+            const bool ac0 = mb0 && (al.x >= 1.0f / 255.0f), ac1 = mb1 && (al.y >= 1.0f / 255.0f);
+            if (!__any_sync(0xffffffffu, ac0 || ac1)) continue;
+
+            const float4 c = rk[2];
+            const float2 ae = f2(ac0 ? al.x : 0.0f, ac1 ? al.y : 0.0f);
+            const float2 Ge = f2(ac0 ? G.x : 0.0f, ac1 ? G.y : 0.0f);
+            const float2 om = fadd2(f2(-ae.x, -ae.y), f2(1.0f));
+            // one reciprocal serves T/(1-a) and T_final/(1-a); 1-a lies in [0.01, 1]: the single-instruction
+            // approximation needs no range fix-up, and rcp(1) = 1 exactly keeps a masked pixel's T untouched
+            float2 inv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(om.x));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(om.y));
+            T = fmul2(T, inv);
+            const float2 w_at = fmul2(ae, T);
+            float2 s_k = ffma2(f2(c.x), dp0, dpa);
+            s_k = ffma2(f2(c.y), dp1, s_k);
+            s_k = ffma2(f2(c.z), dp2, s_k);
+            s_k = ffma2(f2(c.w), dpd, s_k);
+            float2 dLo = fmul2(fadd2(s_k, f2(-accA.x, -accA.y)), T);
+            dLo = ffma2(ntfb, inv, dLo);
+            accA = ffma2(ae, s_k, fmul2(om, accA));  // for the next (nearer) Gaussian
+
+            // With u = dL/dG * G * dx and v = dL/dG * G * dy the mean gradients are -(uA + vB) 0.5W and
+            // -(vC + uB) 0.5H and the conic gradients -0.5 (u dx, u dy, v dy): the per-Gaussian constants
+            // (0.5W, 0.5H, -0.5, the signs) are applied once to the warp sums (slot_scale), not per pixel.
+            const float2 uG = fmul2(fmul2(f2(b.w), dLo), Ge);
+            const float2 u = fmul2(uG, f2(dx)), v = fmul2(uG, dy);
+            const float2 px_ = ffma2(u, f2(b.x), fmul2(v, f2(b.y)));
+            const float2 py_ = ffma2(v, f2(b.z), fmul2(u, f2(b.y)));
+            const float2 ab = ffma2(f2(fabsf(py_.x), fabsf(py_.y)), f2(ddely_dy), fmul2(f2(fabsf(px_.x), fabsf(px_.y)), f2(ddelx_dx)));
+            const float2 udy = fmul2(u, dy), vdy = fmul2(v, dy), gd = fmul2(Ge, dLo);
+            const float2 w0 = fmul2(w_at, dp0), w1 = fmul2(w_at, dp1), w2 = fmul2(w_at, dp2), wd = fmul2(w_at, dpd);
+            float vals[12];
+            vals[0] = px_.x + px_.y;
+            vals[1] = py_.x + py_.y;
+            vals[2] = ab.x + ab.y;
+            vals[3] = (u.x + u.y) * dx;
+            vals[4] = udy.x + udy.y;
+            vals[5] = vdy.x + vdy.y;
+            vals[6] = gd.x + gd.y;
+            vals[7] = w0.x + w0.y;
+            vals[8] = w1.x + w1.y;
+            vals[9] = w2.x + w2.y;
+            vals[10] = wd.x + wd.y;
+            vals[11] = 0.f;
+            const float mine = warp_reduce12_packed(vals, lane) * slot_scale;
+            if (!(lane & 1) && red_slot < 11) atomicAdd(grad_rec + (size_t)gid * GREC + red_slot, mine);
+        }
+    }
+    cp_async_wait_all();
+}
+
 // pixels per lane of the S == 0 backward blend (1 = blend_bwd_kernel<0>); GRPG_BWD_PPL overrides for A/B runs
 static int bwd_pixels_per_lane() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GRPG_BWD_PPL");
         v = e ? atoi(e) : GRPG_BWD_PPL_DEFAULT;
-        if (v != 1 && v != 2) v = GRPG_BWD_PPL_DEFAULT;
+        if (v != 1 && v != 2 && v != 3) v = GRPG_BWD_PPL_DEFAULT;
+    }
+    return v;
+}
+static int bwd_min_blocks() {  // A/B knob of the packed kernel's occupancy target (GRPG_BWD_MINB = 6 | 7 | 8)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GRPG_BWD_MINB");
+        v = e ? atoi(e) : 7;
     }
     return v;
 }
@@ -469,7 +700,16 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
     blend_bwd_wide_kernel<PPLV, MINBV><<<grid, 256 / PPLV, 0, stream>>>(ranges, point_list, rec, a->width, a->height,      \
                                                                  a->background, a->alphas, n_contrib, a->dL_dpix,    \
                                                                  a->dL_dpix_depth, a->dL_dalphas, grad_rec, HL, stride, phase, gfull)
-    if (ppl == 2) GRPG_BWD_WIDE(2, 7);  // 72 registers, 7 CTAs of 4 warps per SM (measured 6: 0.911 ms, 7: 0.912, 8: 0.931)
+#define GRPG_BWD_PACKED(MINBV)                                                                                   \
+    blend_bwd_packed_kernel<MINBV><<<grid, 128, 0, stream>>>(ranges, point_list, rec, a->width, a->height, a->background, \
+                                                             a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth,      \
+                                                             a->dL_dalphas, grad_rec, HL, stride, phase, gfull)
+    if (ppl == 3) {
+        const int mb = bwd_min_blocks();
+        if (mb == 6) GRPG_BWD_PACKED(6);
+        else if (mb == 8) GRPG_BWD_PACKED(8);
+        else GRPG_BWD_PACKED(7);
+    } else if (ppl == 2) GRPG_BWD_WIDE(2, 7);  // 72 registers, 7 CTAs of 4 warps per SM (measured 6: 0.911 ms, 7: 0.912, 8: 0.931)
     else if (S == 0) GRPG_BWD_LAUNCH(0);
     else if (S <= 4) GRPG_BWD_LAUNCH(4);
     else if (S <= 8) GRPG_BWD_LAUNCH(8);
@@ -477,6 +717,7 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
     else GRPG_BWD_LAUNCH(32);
 #undef GRPG_BWD_LAUNCH
 #undef GRPG_BWD_WIDE
+#undef GRPG_BWD_PACKED
 }
 
 }  // namespace grpg

@@ -252,6 +252,14 @@ int grpg_visible_filter(int P, int width, int height,
 int grpg_debug_reference_keys(int P, long long num_rendered, const void* geom_ws,
                               const void* binning_ws, uint64_t* keys_out, void* stream);
 
+/* Test hook for the packed-FP32 blend kernels: evaluates the packed expf restatement (csrc/grpg_common.cuh
+ * `expf2_exact`) and libdevice's expf() on every float bit pattern in [first_bits, last_bits] (as positive-sign or
+ * negative-sign floats per `negative`) and counts the inputs on which the two differ bitwise (NaN results compare
+ * equal); out[0] = mismatches, out[1] = 1 if rcp.approx.ftz(1.0f) == 1.0f exactly (the masking of the packed backward
+ * relies on it), out[2] = inputs evaluated.  `out` = 3 device uint64. */
+int grpg_debug_packed_math_check(uint32_t first_bits, uint32_t last_bits, int negative,
+                                 unsigned long long* out, void* stream);
+
 /* Optional per-kernel timing: between begin and end every kernel this library launches is
  * bracketed by CUDA events on its launching stream.  grpg_profile_end synchronises and writes
  * "name:launches:total_ms" lines into buf.  Used by bench.py for the roofline object only. */
