@@ -143,23 +143,33 @@ def make_step_fns(dgr, sc, gt, w_depth, w_alpha):
     return fwd_only, fwd_bwd, leaves
 
 
-def time_region(fn, steps, dist_on):
+def time_region(fn, steps, dist_on, per_step=None):
+    """Total device time of `steps` calls (CUDA events on the current stream, a synchronize on both sides).  With
+    `per_step` (a list) an event is also recorded after every call and the individual step times are appended."""
     import torch.distributed as dist
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
         fn()
-    e1.record()
+        ev[i + 1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms = ev[0].elapsed_time(ev[steps])
+    if per_step is not None:
+        per_step.extend(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
     if dist_on:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return ms
+
+
+def percentiles(xs):
+    xs = sorted(xs)
+    q = lambda f: xs[min(len(xs) - 1, max(0, int(round(f * (len(xs) - 1)))))]  # noqa: E731
+    return {"median": q(0.5), "p10": q(0.1), "p90": q(0.9), "n": len(xs)}
 
 
 def cpu_baseline_sample(sc_cpu, n_tiles=96):
@@ -183,11 +193,59 @@ def cpu_baseline_sample(sc_cpu, n_tiles=96):
     torch.set_num_threads(min(8, os.cpu_count() or 1))
     secs, n_inst, n_done = torch_blend.time_tiles(pre, binned, sc_cpu, [int(t) for t in picks], budget_s=20.0)
     est_total = secs / max(1, n_inst) * float(lens.sum()) + t_pre
+    try:
+        affinity = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        affinity = os.cpu_count()
     return {"value": 1.0 / est_total, "unit": "iters/s", "cores": torch.get_num_threads(), "kind": "port",
+            "host_cores": os.cpu_count(), "host_cores_usable": affinity,
             "sample": f"pure-PyTorch per-pixel blend fwd+autograd-bwd of {n_done} random tiles ({n_inst} of {int(lens.sum())} "
                       f"tile instances) in {secs:.1f} s + C-oracle preprocess/sort of the full scene in {t_pre:.1f} s; "
                       f"blend time extrapolated per instance to the full frame",
             "seconds_measured": round(secs + t_pre, 2)}
+
+
+def parity_vs_reference(sc, ours_fwd, dev):
+    """Checker leg (not timed, not part of the product path): the same scene through the UNMODIFIED reference extension
+    (oracle/_ref) -- differing floats / max abs / PSNR of the images of the product path, index mismatches in
+    reference-binning mode, max relative gradient error per tensor.  None when oracle/_ref is not present."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    sys.path.insert(0, str(ROOT / "tests"))
+    try:
+        import build_ref
+        if not build_ref.available():
+            return None
+        import cases
+        import refparse
+        from gaussianrpg_b200 import _C, debug as _dbg
+        ref = build_ref.load()
+        P, W, H = sc.means3D.shape[0], sc.width, sc.height
+        rf = cases.raw_forward(ref._C, sc)
+        out = {"images": {}}
+        for i, k in ((1, "color"), (2, "depth"), (3, "alpha")):
+            d = (ours_fwd[i] - rf[i]).abs()
+            mse = float((d.double() ** 2).mean())
+            out["images"][k] = {"differing_floats": int((ours_fwd[i] != rf[i]).sum()), "max_abs": float(d.max()),
+                                "psnr_db": None if mse == 0 else round(10 * __import__("math").log10(1.0 / mse), 1)}
+        out["num_rendered_equal"] = bool(ours_fwd[0] == rf[0])
+        out["radii_mismatches"] = int((ours_fwd[5] != rf[5]).sum())
+        rb = cases.raw_forward(_C, sc, _reference_binning=True)
+        a = _dbg.parse_buffers(P, rb[0], W, H, rb[6], rb[7], rb[8])
+        b = refparse.parse_reference(P, rf[0], W, H, rf[6], rf[7], rf[8])
+        out["index_mismatches"] = {k: int((a[k] != b[k]).sum()) for k in ("tiles_touched", "point_list", "point_list_keys",
+                                                                         "ranges", "n_contrib")}
+        del rb, a, b
+        g = torch.Generator().manual_seed(7)
+        dL = [torch.randn(3, H, W, generator=g).to(dev), (torch.randn(1, H, W, generator=g) * 0.1).to(dev),
+              torch.randn(1, H, W, generator=g).to(dev), torch.zeros(0, H, W, device=dev)]
+        go = cases.raw_backward(_C, sc, ours_fwd, dL)
+        gr = cases.raw_backward(ref._C, sc, rf, dL)
+        out["grad_max_rel"] = {n: float((x - y).abs().max() / y.abs().max().clamp_min(1e-30))
+                               for n, x, y in zip(cases.GRAD_NAMES, go, gr) if x.numel()}
+        out["vs"] = "unmodified reference extension (oracle/_ref), same inputs, same device"
+        return out
+    except Exception as exc:  # the checker must never cost the measurement
+        return {"error": repr(exc)}
 
 
 def main():
@@ -253,10 +311,11 @@ def main():
     for _ in range(max(args.warmup, 3)):
         fwd_bwd(view, proj, campos, gt_dev)
     clocks = ClockSampler(local_rank)
-    ms_fb = time_region(lambda: fwd_bwd(view, proj, campos, gt_dev), args.steps, False)
+    steps_fb, steps_f = [], []
+    ms_fb = time_region(lambda: fwd_bwd(view, proj, campos, gt_dev), args.steps, False, steps_fb)
     for _ in range(3):
         fwd_only(view, proj, campos)
-    ms_f = time_region(lambda: fwd_only(view, proj, campos), args.steps, False)
+    ms_f = time_region(lambda: fwd_only(view, proj, campos), args.steps, False, steps_f)
 
     # ---- end to end: per-step host inputs in, result out ---------------------------------------
     # The camera is needed before the first kernel; the ground-truth image only by the loss, so its upload runs on
@@ -272,6 +331,29 @@ def main():
             gt_ready = copy_stream.record_event()
         loss = fwd_bwd(cam[:16].view(4, 4), cam[16:32].view(4, 4), cam[32:35], gt, gt_ready)
         return float(loss.item())  # D2H read of the step's result
+
+    # The same step with the loader one step ahead (what a prefetching DataLoader does): the upload of step i+1's
+    # ground truth is issued at the start of step i into the other of two device buffers, so the 29.5 MB copy
+    # (1.3 ms at this box's 22 GB/s host link -- longer than the forward) overlaps step i instead of stalling its
+    # loss.  Every step still copies its camera and one ground-truth image inside the timed region and reads its loss
+    # back; one extra image is uploaded before the region starts.
+    gt_buf = [torch.empty_like(gt_dev), torch.empty_like(gt_dev)]
+    gt_evt = [None, None]
+    pf_state = {"i": 0}
+
+    def prefetch(slot):
+        copy_stream.wait_stream(torch.cuda.current_stream())  # the buffer's previous reader (two steps back) is done
+        with torch.cuda.stream(copy_stream):
+            gt_buf[slot].copy_(gt_host, non_blocking=True)
+            gt_evt[slot] = copy_stream.record_event()
+
+    def e2e_fb_prefetch():
+        i = pf_state["i"]
+        pf_state["i"] = i + 1
+        cam = cam_host.to(dev, non_blocking=True)
+        prefetch((i + 1) & 1)
+        loss = fwd_bwd(cam[:16].view(4, 4), cam[16:32].view(4, 4), cam[32:35], gt_buf[i & 1], gt_evt[i & 1])
+        return float(loss.item())
 
     img_host = torch.empty(3, H, W).pin_memory()
 
@@ -302,7 +384,12 @@ def main():
 
     for _ in range(3):
         e2e_fb(); e2e_f(); e2e_rgb8()
-    ms_e2e_fb = time_region(e2e_fb, args.steps, False)
+    ms_e2e_fb_serial = time_region(e2e_fb, args.steps, False)
+    prefetch(0)
+    for _ in range(3):
+        e2e_fb_prefetch()
+    steps_e2e = []
+    ms_e2e_fb = time_region(e2e_fb_prefetch, args.steps, False, steps_e2e)
     ms_e2e_f = time_region(e2e_f, args.steps, False)
     ms_e2e_rgb8 = time_region(e2e_rgb8, args.steps, False)
     clk = clocks.stop()
@@ -324,14 +411,23 @@ def main():
                                "depth_order_is_permutation": _perm,
                                "keys_sorted": bool((_p["point_list_keys"][1:] >= _p["point_list_keys"][:-1]).all())}
 
+        base["index_check"]["note"] = ("product binning bins a subset of the reference's instances (those whose alpha can "
+                                       "reach 1/255), in the reference's order; element-for-element index equality is "
+                                       "measured in reference-binning mode (parity.index_mismatches)")
+        base["parity"] = parity_vs_reference(sc, raw, dev)
+
     result = dict(base)
     result.update(
         value=1000.0 * args.steps / ms_fb, ms_per_step=ms_fb / args.steps,
-        fwd_fps=1000.0 * args.steps / ms_f, fwd_ms=ms_f / args.steps,
+        ms_per_step_stats=percentiles(steps_fb),
+        fwd_fps=1000.0 * args.steps / ms_f, fwd_ms=ms_f / args.steps, fwd_ms_stats=percentiles(steps_f),
         e2e={"value": 1000.0 * args.steps / ms_e2e_fb, "unit": "iters/s",
              "h2d_bytes_per_step": int(cam_host.numel() * 4 + gt_host.numel() * 4), "d2h_bytes_per_step": 4,
-             "note": "camera (35 floats) + ground-truth image H2D from pinned memory (image upload on a copy stream, "
-                     "joined before the loss), loss scalar D2H; Gaussian parameters are model state resident in HBM"},
+             "note": "per step: camera (35 floats) + one ground-truth image H2D from pinned memory, loss scalar D2H; the "
+                     "image upload runs on a copy stream one step ahead (double-buffered prefetch, as a DataLoader "
+                     "does) and is joined before the loss; Gaussian parameters are model state resident in HBM",
+             "ms_per_step": percentiles(steps_e2e),
+             "value_without_prefetch": 1000.0 * args.steps / ms_e2e_fb_serial},
         e2e_fwd={"value": 1000.0 * args.steps / ms_e2e_f, "unit": "frames/s", "h2d_bytes_per_step": int(cam_host.numel() * 4),
                  "d2h_bytes_per_step": int(img_host.numel() * 4)},
         e2e_fwd_rgb8={"value": 1000.0 * args.steps / ms_e2e_rgb8, "unit": "frames/s",
@@ -339,8 +435,7 @@ def main():
                       "d2h_bytes_per_step": int(H * W * 3 if args.impl == "ours" else img_host.numel() * 4),
                       "note": "clamped frame delivered to the host as uint8 HWC (what simulator.py:313-314 produces)"},
         clocks={"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
-        config={"workload": workload, "P": P, "V": V, "R": R,
-                "R_binned": base.get("index_check", {}).get("binned", R), "width": W, "height": H,
+        config={"workload": workload, "P": P, "V": V, "R": R, "width": W, "height": H,
                 "l2": "no flush: one step streams > 126 MB (record table 48 B*P, 16 B*R instance lists, images)",
                 "timing": "CUDA events on the current stream around K steps after W warm-up steps"},
     )
@@ -397,8 +492,8 @@ def main():
                 result["cpu_baseline"] = {"error": repr(exc)}
     else:
         result["gpu_launches"] = 0
-        result["config"]["reference_note"] = ("the reference op is single-GPU (no distributed path exists in it): this arm "
-                                              "always runs on one B200, n_gpus echoes the launch size")
+        result["reference_note"] = ("the reference op is single-GPU (no distributed path exists in it): this arm "
+                                    "always runs on one B200, n_gpus echoes the launch size")
         result["cpu_baseline"] = {"value": result["value"], "unit": "iters/s", "cores": 0, "kind": "reference",
                                   "sample": "full workload on the same B200: the reference's only implementation of this "
                                             "path is its CUDA extension (no CPU code path exists)"}

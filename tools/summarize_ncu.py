@@ -38,6 +38,14 @@ for r in rows[2:]:
         except ValueError:
             continue
         d[k] = round(v * (scale_bytes(units[i]) if sc is None else sc), 3)
+    # every per-pipe utilisation metric the report holds (names differ between architectures)
+    d["pipes"] = {}
+    for i, m in enumerate(hdr):
+        if "inst_executed_pipe_" in m and m.endswith("pct_of_peak_sustained_active"):
+            try:
+                d["pipes"][m.split("inst_executed_pipe_")[1].split(".")[0]] = round(float(r[i]), 2)
+            except ValueError:
+                pass
     res.append(d)
 json.dump(res, open(out + ".json", "w"), indent=1)
 keys = ["kernel", "time_us", "issue_active_pct", "dram_throughput_pct", "dram_read_MB", "dram_write_MB", "warps_active_pct",
