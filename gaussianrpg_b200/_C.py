@@ -18,6 +18,37 @@ NUM_CHANNELS = 3
 _NEED_BINNING = 2   # GRPG_NEED_BINNING (include/grpg_b200.h)
 _last_binned = {}    # (P, W, H, band, device) -> instances binned by the previous call: sizes the next workspace
 
+# ---- static-capacity mode (grpg_forward_static): no host synchronisation, CUDA-graph capturable --------------------
+_static_capacity = None   # instances; None = the default path (one host sync per forward, exact workspace)
+_static_counts = {}       # key -> pinned int64[4] (num_binned, num_rendered, overflow, depth-sorted Gaussians) of the
+#                           last static forward with that key; written asynchronously on the forward's stream
+
+
+def set_static_binning(capacity):
+    """Switch every following forward of this process to the sync-free path with room for `capacity` Gaussian/tile
+    instances (None switches back).  The forward then never waits for the device -- the reference blocks on a
+    device-to-host copy of num_rendered (rasterizer_impl.cu:284), and so does the default path here -- which makes
+    a whole training step capturable into a CUDA graph.  A frame that needs more instances than `capacity` is rendered
+    incompletely and flagged: call `check_static_binning()` after a synchronisation point (e.g. right after reading
+    the loss) -- it raises with the capacity that was needed."""
+    global _static_capacity
+    _static_capacity = None if capacity is None else int(capacity)
+    return _static_capacity
+
+
+def static_binning_counts():
+    """{key: (num_binned, num_rendered, overflow, depth_sorted)} of the last static forwards; valid after the stream
+    they ran on has been synchronised."""
+    return {k: tuple(int(x) for x in v) for k, v in _static_counts.items()}
+
+
+def check_static_binning():
+    """Raise if any static forward since the last call overflowed its capacity (call after a synchronisation)."""
+    for k, v in _static_counts.items():
+        if int(v[2]) != 0:
+            raise RuntimeError(f"static binning capacity {_static_capacity} exceeded: the frame needs {int(v[0])} "
+                               f"instances (forward key {k}); call set_static_binning() with a larger capacity")
+
 
 _cuda_ok = None
 
@@ -67,7 +98,7 @@ def _layouts(P: int, R: int, W: int, H: int):
 def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
                         degree, campos, prefiltered, debug, *, _band=(1, 0), _forward_only=False, _peer_frames=None,
-                        _reference_binning=False) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
+                        _reference_binning=False, _static=None) -> Tuple[int, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
                                    torch.Tensor, torch.Tensor, torch.Tensor]:
     """RasterizeGaussiansCUDA (rasterize_points.cu:35-124).
 
@@ -79,7 +110,9 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
     (gaussianrpg_b200.dist reassembles them).  `_reference_binning=True` bins exactly the reference's tile
     rectangles (index buffers then equal the reference's element for element); by default rectangles are clipped
     to the alpha >= 1/255 footprint, which drops instances the reference sorts and then skips.  `num_rendered` is
-    the reference's count either way.
+    the reference's count either way.  `_static=capacity` (default: the process-wide `set_static_binning` value) runs
+    the sync-free path; the returned num_rendered is then `capacity` (an upper bound that grpg_backward accepts), the
+    true counts land in `static_binning_counts()`.
     """
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:58-60
@@ -150,12 +183,26 @@ def rasterize_gaussians(background, means3D, colors, semantics, opacity, scales,
         for i, ptr in enumerate(_peer_frames):
             a.peer_frames[i] = int(ptr)
 
+    key = (P, W, H, stride, phase, bool(_reference_binning), dev.index)
+    bl = _lib.BinningLayout()
+    static_cap = _static_capacity if _static is None else (int(_static) or None)
+    if static_cap and not debug:
+        lib.grpg_get_binning_layout(static_cap, C.byref(bl))
+        binning = torch.empty(max(int(bl.total_bytes), 256), **u8)
+        a.binning_ws = _ptr(binning)
+        counts = _static_counts.get(key)
+        if counts is None:
+            counts = _static_counts[key] = torch.zeros(4, dtype=torch.int64).pin_memory()
+            if len(_static_counts) > 64:
+                _static_counts.pop(next(iter(_static_counts)))
+        with torch.cuda.device(dev):
+            _check(lib.grpg_forward_static(C.byref(a), static_cap, counts.data_ptr()))
+        return static_cap, out_color, out_depth, out_alpha, out_semantic, radii, geom, binning, img
+
     # The binning workspace is sized by a device-side count.  Guess it from the previous call with the same shape
     # (+25 %), so that both stages run inside one library call and the render stage is launched right behind the
     # host sync; when the guess is too small the library stops after the geometry stage and the exact size is used.
-    key = (P, W, H, stride, phase, bool(_reference_binning), dev.index)
     guess = _last_binned.get(key, 0)
-    bl = _lib.BinningLayout()
     lib.grpg_get_binning_layout(int(guess * 1.25) + 4096, C.byref(bl))
     binning = torch.empty(max(int(bl.total_bytes), 256), **u8)  # never empty: backward needs a valid pointer
     a.binning_ws = _ptr(binning)

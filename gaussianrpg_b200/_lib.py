@@ -116,6 +116,7 @@ SYMBOLS = {
     "grpg_forward_geometry": (C.c_int, [C.POINTER(ForwardArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "grpg_forward_render": (C.c_int, [C.POINTER(ForwardArgs), C.c_int]),
     "grpg_forward": (C.c_int, [C.POINTER(ForwardArgs), C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "grpg_forward_static": (C.c_int, [C.POINTER(ForwardArgs), C.c_longlong, _fp]),
     "grpg_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "grpg_backward": (C.c_int, [C.POINTER(BackwardArgs)]),
     "grpg_mark_visible": (C.c_int, [C.c_int, _fp, _fp, _fp, _fp, _fp]),

@@ -20,11 +20,12 @@ size_t geom_scratch_bytes(int P);
 size_t binning_scratch_bytes(long long R);
 unsigned long long* prepare_geometry_scratch(int P, void* scratch, cudaStream_t stream);
 void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, const uint32_t* tiles_touched,
-                              uint32_t* offsets, void* scratch, unsigned long long* num_rendered_dev, int num_sms,
-                              cudaStream_t stream);
+                              uint32_t* offsets, void* scratch, unsigned long long* counts, unsigned long long capacity,
+                              int num_sms, cudaStream_t stream);
 void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tiles, const uint32_t* sorted_idx,
                           const uint32_t* offsets, const uint2* rect, const void* geom_scratch, uint32_t* tile_keys,
-                          uint32_t* point_list, void* scratch, uint2* ranges, int num_sms, cudaStream_t stream);
+                          uint32_t* point_list, void* scratch, uint2* ranges, const unsigned long long* counts,
+                          int static_capacity, int num_sms, cudaStream_t stream);
 void launch_reference_keys(long long R, const uint32_t* point_list, const uint32_t* tile_keys, const Rec* rec,
                            unsigned long long* keys, cudaStream_t stream);
 void launch_packed_math_check(uint32_t first_bits, uint32_t last_bits, int negative, unsigned long long* out,
@@ -152,7 +153,7 @@ int grpg_get_geometry_layout(int P, grpg_geom_layout* out) {
     out->sorted_idx = take(p * 4);
     out->offsets = take(p * 4);
     out->scratch = take(geom_scratch_bytes(P));
-    out->num_rendered = take(16);
+    out->num_rendered = take(64);
     out->total_bytes = o;
     return 0;
 }
@@ -202,12 +203,8 @@ static int validate_forward(const grpg_forward_args* a) {
     return 0;
 }
 
-int grpg_forward_geometry(const grpg_forward_args* a, int* num_binned, int* num_rendered) {
-    if (!num_binned) return fail("null num_binned");
-    *num_binned = 0;
-    if (num_rendered) *num_rendered = 0;
-    if (int rc = validate_forward(a)) return rc;
-    if (a->P == 0) return 0;
+// launches of stage 1 (no synchronisation)
+static int launch_forward_geometry(const grpg_forward_args* a, unsigned long long capacity) {
     cudaStream_t stream = (cudaStream_t)a->stream;
     grpg_geom_layout L;
     grpg_get_geometry_layout(a->P, &L);
@@ -222,9 +219,22 @@ int grpg_forward_geometry(const grpg_forward_args* a, int* num_binned, int* num_
     if (a->debug) if (int rc = check_cuda("preprocess", true, stream)) return rc;
     run_depth_order_and_scan(a->P, (uint32_t*)(g + L.depth_key), (uint32_t*)(g + L.sorted_idx),
                              (const uint32_t*)(g + L.tiles_touched), (uint32_t*)(g + L.offsets), g + L.scratch,
-                             (unsigned long long*)(g + L.num_rendered), device_sm_count(), stream);
+                             (unsigned long long*)(g + L.num_rendered), capacity, device_sm_count(), stream);
+    return 0;
+}
+
+int grpg_forward_geometry(const grpg_forward_args* a, int* num_binned, int* num_rendered) {
+    if (!num_binned) return fail("null num_binned");
+    *num_binned = 0;
+    if (num_rendered) *num_rendered = 0;
+    if (int rc = validate_forward(a)) return rc;
+    if (a->P == 0) return 0;
+    cudaStream_t stream = (cudaStream_t)a->stream;
+    if (int rc = launch_forward_geometry(a, 0)) return rc;
+    grpg_geom_layout L;
+    grpg_get_geometry_layout(a->P, &L);
     unsigned long long* host = pinned_word();
-    cudaMemcpyAsync(host, g + L.num_rendered, 16, cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(host, (char*)a->geom_ws + L.num_rendered, 16, cudaMemcpyDeviceToHost, stream);
     if (int rc = check_cuda("forward_geometry", true, stream)) return rc;
     if (host[0] >= (1ull << 31) || host[1] >= (1ull << 31)) return fail("too many Gaussian/tile instances (>= 2^31, the range of the reference's int num_rendered)");
     *num_binned = (int)host[0];
@@ -232,8 +242,7 @@ int grpg_forward_geometry(const grpg_forward_args* a, int* num_binned, int* num_
     return 0;
 }
 
-int grpg_forward_render(const grpg_forward_args* a, int num_rendered) {
-    if (int rc = validate_forward(a)) return rc;
+static int forward_render_impl(const grpg_forward_args* a, long long num_rendered, int static_capacity) {
     cudaStream_t stream = (cudaStream_t)a->stream;
     const int stride = a->tile_row_stride > 1 ? a->tile_row_stride : 1, phase = a->tile_row_stride > 1 ? a->tile_row_phase : 0;
     grpg_image_layout IL;
@@ -251,11 +260,17 @@ int grpg_forward_render(const grpg_forward_args* a, int num_rendered) {
     run_instance_binning(a->P, num_rendered, gx, gx * gy, (const uint32_t*)(g + L.sorted_idx),
                          (const uint32_t*)(g + L.offsets), (const uint2*)(g + L.rect), g + L.scratch,
                          b ? (uint32_t*)(b + BL.tile_keys) : nullptr, b ? (uint32_t*)(b + BL.point_list) : nullptr,
-                         b ? b + BL.scratch : nullptr, (uint2*)(im + IL.ranges), device_sm_count(), stream);
+                         b ? b + BL.scratch : nullptr, (uint2*)(im + IL.ranges),
+                         (const unsigned long long*)(g + L.num_rendered), static_capacity, device_sm_count(), stream);
     if (a->debug) if (int rc = check_cuda("binning", true, stream)) return rc;
     launch_blend_fwd(a, (const uint2*)(im + IL.ranges), b ? (const uint32_t*)(b + BL.point_list) : nullptr,
                      (const Rec*)(g + L.rec), (uint32_t*)(im + IL.n_contrib), stream);
     return check_cuda("forward_render", a->debug != 0, stream);
+}
+
+int grpg_forward_render(const grpg_forward_args* a, int num_rendered) {
+    if (int rc = validate_forward(a)) return rc;
+    return forward_render_impl(a, num_rendered, 0);
 }
 
 int grpg_forward(const grpg_forward_args* a, size_t binning_capacity_bytes, int* num_binned, int* num_rendered) {
@@ -264,6 +279,25 @@ int grpg_forward(const grpg_forward_args* a, size_t binning_capacity_bytes, int*
     grpg_get_binning_layout(*num_binned, &BL);
     if (*num_binned > 0 && (!a->binning_ws || BL.total_bytes > binning_capacity_bytes)) return GRPG_NEED_BINNING;
     return grpg_forward_render(a, *num_binned);
+}
+
+int grpg_forward_static(const grpg_forward_args* a, long long capacity, unsigned long long* counts_host) {
+    if (int rc = validate_forward(a)) return rc;
+    if (capacity <= 0 || capacity >= (1ll << 31)) return fail("grpg_forward_static: capacity must lie in [1, 2^31)");
+    if (a->debug) return fail("grpg_forward_static: debug mode synchronises; use grpg_forward");
+    if (a->P == 0) return 0;
+    if (!a->binning_ws) return fail("missing binning workspace");
+    cudaStream_t stream = (cudaStream_t)a->stream;
+    if (int rc = launch_forward_geometry(a, (unsigned long long)capacity)) return rc;
+    if (int rc = forward_render_impl(a, capacity, 1)) return rc;
+    if (counts_host) {
+        grpg_geom_layout L;
+        grpg_get_geometry_layout(a->P, &L);
+        cudaMemcpyAsync(counts_host, (const char*)a->geom_ws + L.num_rendered, 32, cudaMemcpyDeviceToHost, stream);
+    }
+    cudaError_t e = cudaGetLastError();  // launch-configuration errors only; nothing here waits for the device
+    if (e != cudaSuccess) return fail(std::string("[CUDA ERROR] in forward_static: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 size_t grpg_backward_workspace_bytes(int P, int S) {

@@ -35,19 +35,29 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 }
 
 __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restrict__ sorted_idx,
-                                                         const uint32_t* __restrict__ tiles_touched, uint32_t P,
+                                                         const uint32_t* __restrict__ tiles_touched, uint32_t P_cap,
                                                          uint32_t* __restrict__ offsets,
                                                          unsigned long long* __restrict__ status /*[tiles+1]*/,
                                                          uint32_t* __restrict__ tile_counter,
                                                          unsigned long long* __restrict__ total_out,
                                                          const unsigned long long* __restrict__ ref_instances,
-                                                         uint32_t* __restrict__ chunk_start) {
+                                                         uint32_t* __restrict__ chunk_start,
+                                                         unsigned long long capacity) {
     __shared__ uint32_t s_scan[8];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_excl;
+    // total_out = the forward's device-side counters: [0] instances to bin, [1] the reference's num_rendered,
+    // [2] overflow flag of the static-capacity mode, [3] Gaussians in the depth order (written by the depth sort's
+    // compacting first pass; the grid of this kernel covers all P_cap, tiles past the count leave at once)
+    const uint32_t P = (uint32_t)min((unsigned long long)P_cap, total_out[3]);
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (P == 0) {  // nothing visible: the first ticket publishes the (zero) totals
+        if (tile == 0 && threadIdx.x == 0) { total_out[0] = 0; total_out[1] = *ref_instances; total_out[2] = 0; }
+        return;
+    }
+    if ((unsigned long long)tile * SCAN_TILE >= P) return;
     const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
     uint32_t v[SCAN_IPT];
     uint32_t sum = 0;
@@ -90,6 +100,7 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
             if ((tile + 1) * (unsigned long long)SCAN_TILE >= P) {
                 total_out[0] = excl + block_total;  // instances to bin
                 total_out[1] = *ref_instances;       // instances the reference would bin (its num_rendered)
+                total_out[2] = (capacity != 0 && excl + block_total > capacity) ? 1ull : 0ull;
             }
         }
     }
@@ -102,7 +113,7 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
             offsets[j] = run;
             // every multiple of EMIT_CHUNK inside [run, run + v) starts in sorted position j
             for (uint32_t kb = (run + EMIT_CHUNK - 1) / EMIT_CHUNK; (unsigned long long)kb * EMIT_CHUNK < (unsigned long long)run + v[i]; ++kb)
-                chunk_start[kb] = j;
+                if (kb < EMIT_MAX_CHUNKS) chunk_start[kb] = j;
         }
         run += v[i];
     }
@@ -117,7 +128,8 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __r
                                                              const uint32_t* __restrict__ offsets,
                                                              const uint2* __restrict__ rect,
                                                              const uint32_t* __restrict__ chunk_start, uint32_t P,
-                                                             uint32_t R, uint32_t grid_x,
+                                                             uint32_t R, const unsigned long long* __restrict__ counts,
+                                                             uint32_t grid_x,
                                                              uint32_t* __restrict__ inst_tile,
                                                              uint32_t* __restrict__ inst_gauss,
                                                              uint32_t* __restrict__ tile_hist /*[256][sort tiles]*/,
@@ -128,6 +140,10 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __r
     s_hist[0][threadIdx.x] = 0;
     s_hist[1][threadIdx.x] = 0;
     __syncthreads();
+    if (counts != nullptr) {  // static-capacity mode: the counts live on the device, R and P are capacities
+        R = (uint32_t)min((unsigned long long)R, counts[0]);
+        P = (uint32_t)min((unsigned long long)P, counts[3]);
+    }
     const int lane = threadIdx.x & 31;
     const int half = (threadIdx.x >> 5) >> 2;  // warps 0-3 -> first sort tile, 4-7 -> second
     const uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -182,7 +198,9 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __r
 
 // ---- 5. tile ranges (identifyTileRanges, rasterizer_impl.cu:116-138) -----------------------
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ tile_keys, uint32_t R,
-                                                          uint2* __restrict__ ranges) {
+                                                          uint2* __restrict__ ranges,
+                                                          const unsigned long long* __restrict__ counts) {
+    if (counts != nullptr) R = (uint32_t)min((unsigned long long)R, counts[0]);
     // 4 keys per thread (one 16-byte load) + the key before them
     const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i0 >= R) return;
@@ -252,10 +270,13 @@ unsigned long long* prepare_geometry_scratch(int P, void* scratch, cudaStream_t 
     return (unsigned long long*)(p + status_bytes + 64);  // counters block: [0] scan tile ticket, [64] ref instances
 }
 
-// Steps 1-2.  depth_key is consumed (left sorted); sorted_idx receives the permutation.
+// Steps 1-2.  depth_key is consumed (left sorted); sorted_idx receives the permutation of the Gaussians that emit at
+// least one instance (tiles_touched != 0) -- the sort's first digit pass drops the others for free, so the remaining
+// passes, the scan and the emission work on the visible (and, with tile-row bands, in-band) Gaussians only.
+// `counts` = the forward's device-side counters (see scan_tiles_kernel).
 void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, const uint32_t* tiles_touched,
-                              uint32_t* offsets, void* scratch, unsigned long long* num_rendered_dev, int num_sms,
-                              cudaStream_t stream) {
+                              uint32_t* offsets, void* scratch, unsigned long long* counts, unsigned long long capacity,
+                              int num_sms, cudaStream_t stream) {
     char* p = (char*)scratch;
     uint32_t* keys_b = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
     uint32_t* vals_b = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
@@ -271,7 +292,8 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
     // values start as the identity permutation: generated inside the first digit pass, no iota kernel
     bool in_a = onesweep_sort_pairs(depth_key, sorted_idx, keys_b, vals_b, P, 32, aux, num_sms, stream,
                                     "depth_sort_hist", "depth_sort_scan", "depth_sort_pass", /*iota_values=*/true,
-                                    /*first_hist_ready=*/false, /*gather_src=*/tiles_touched, /*gather_dst=*/offsets);
+                                    /*first_hist_ready=*/false, /*gather_src=*/tiles_touched, /*gather_dst=*/offsets,
+                                    /*n_dev=*/nullptr, /*keep_src=*/tiles_touched, /*n_kept_out=*/counts + 3);
     if (!in_a) {  // 32 bits -> 4 passes -> always lands back in the a-buffers; kept for safety
         cudaMemcpyAsync(depth_key, keys_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(sorted_idx, vals_b, (size_t)P * 4, cudaMemcpyDeviceToDevice, stream);
@@ -279,14 +301,17 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
     // status words and counters were zeroed by prepare_geometry_scratch
     ProfScope ps("scan_tiles", stream);
     scan_tiles_kernel<<<(unsigned)scan_tiles, 256, 0, stream>>>(
-        sorted_idx, tiles_touched, (uint32_t)P, offsets, status, scan_counter, num_rendered_dev,
-        (const unsigned long long*)((const char*)scan_counter + 64), chunk_start);
+        sorted_idx, tiles_touched, (uint32_t)P, offsets, status, scan_counter, counts,
+        (const unsigned long long*)((const char*)scan_counter + 64), chunk_start, capacity);
 }
 
-// Steps 3-5.  Final order lands in (tile_keys, point_list).
+// Steps 3-5.  Final order lands in (tile_keys, point_list).  `R` is the instance count when the host knows it
+// (counts_are_exact) or the capacity of the binning workspace in static-capacity mode, where every kernel reads the
+// count from `counts` on the device and the grids cover the capacity.
 void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tiles, const uint32_t* sorted_idx,
                           const uint32_t* offsets, const uint2* rect, const void* geom_scratch, uint32_t* tile_keys,
-                          uint32_t* point_list, void* scratch, uint2* ranges, int num_sms, cudaStream_t stream) {
+                          uint32_t* point_list, void* scratch, uint2* ranges, const unsigned long long* counts,
+                          int static_capacity, int num_sms, cudaStream_t stream) {
     cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), stream);
     if (R <= 0) return;
     char* p = (char*)scratch;
@@ -310,18 +335,18 @@ void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tile
         gs += align_up((size_t)SORT_MAX_PASSES * (256 + 64) * 4 + (size_t)SORT_MAX_PASSES * sort_num_tiles(P) * 256 * 4, 256);
         gs += align_up((((size_t)P + SCAN_TILE - 1) / SCAN_TILE + 2) * 8, 256) + 256;
         const uint32_t* chunk_start = (const uint32_t*)gs;
-        const unsigned warps = (unsigned)((R + EMIT_CHUNK - 1) / EMIT_CHUNK);
         static_assert(EMIT_CHUNK * 8 == 2 * SORT_TILE, "an emit CTA must cover exactly two sort tiles");
         const uint32_t sort_tiles = (uint32_t)sort_num_tiles(R);
         emit_instances_kernel<<<(sort_tiles + 1) / 2, 256, 0, stream>>>(
-            sorted_idx, offsets, rect, chunk_start, (uint32_t)P, (uint32_t)R, grid_x, k0, v0, sort_first_pass_hist(aux),
-            sort_tiles, (1u << plan.bits[0]) - 1u);
-        (void)warps;
+            sorted_idx, offsets, rect, chunk_start, (uint32_t)P, (uint32_t)R, counts, grid_x, k0, v0,
+            sort_first_pass_hist(aux), sort_tiles, (1u << plan.bits[0]) - 1u);
     }
     onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream, "tile_sort_hist", "tile_sort_scan", "tile_sort_pass",
-                        /*iota_values=*/false, /*first_hist_ready=*/true);
+                        /*iota_values=*/false, /*first_hist_ready=*/true, nullptr, nullptr,
+                        /*n_dev=*/static_capacity ? counts : nullptr);
     ProfScope ps("tile_ranges", stream);
-    tile_ranges_kernel<<<(unsigned)((R + 1023) / 1024), 256, 0, stream>>>(tile_keys, (uint32_t)R, ranges);
+    tile_ranges_kernel<<<(unsigned)((R + 1023) / 1024), 256, 0, stream>>>(tile_keys, (uint32_t)R, ranges,
+                                                                          static_capacity ? counts : nullptr);
 }
 
 void launch_reference_keys(long long R, const uint32_t* point_list, const uint32_t* tile_keys, const Rec* rec,

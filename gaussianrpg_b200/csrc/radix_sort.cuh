@@ -108,7 +108,10 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift, int bits,
     const uint32_t* __restrict__ hist /*[256] for this pass*/, uint32_t* __restrict__ tile_counter,
     uint32_t* __restrict__ lookback /*[tiles][256]*/, int iota_values, int precomputed_offsets,
-    const uint32_t* __restrict__ gather_src, uint32_t* __restrict__ gather_dst) {
+    const uint32_t* __restrict__ gather_src, uint32_t* __restrict__ gather_dst,
+    const unsigned long long* __restrict__ n_dev /* device-side element count (clamped to n) or NULL */,
+    const uint32_t* __restrict__ keep_src /* pass 0 only: element i takes part iff keep_src[i] != 0, or NULL */,
+    unsigned long long* __restrict__ n_out /* receives the number of elements written (the kept ones) or NULL */) {
     __shared__ uint32_t s_warp_hist[8][256];
     __shared__ uint32_t s_local_start[256];
     __shared__ uint32_t s_bin_base[256];
@@ -119,6 +122,11 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mask = (1u << bits) - 1u;
+    if (n_dev != nullptr) {  // the count lives on the device (no host sync): the grid covers the capacity `n`
+        const unsigned long long nd = *n_dev;
+        n = nd < n ? (uint32_t)nd : n;
+        if (blockIdx.x * (uint32_t)SORT_TILE >= n && !(blockIdx.x == 0 && n_out != nullptr)) return;
+    }
     // look-back mode needs tile ids in scheduling order; with precomputed offsets the block index will do
     if (tid == 0) s_tile = precomputed_offsets ? blockIdx.x : atomicAdd(tile_counter, 1u);
 #pragma unroll
@@ -130,10 +138,12 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
 
     uint32_t key[SORT_IPT], val[SORT_IPT];
     uint16_t rank[SORT_IPT];
+    uint32_t keep_bits = 0xFFFFu;  // bit i: item i of this thread takes part (pass-0 compaction drops the others)
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
         uint32_t idx = warp_base + i * 32 + lane;
         key[i] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
+        if (keep_src != nullptr && !(idx < n && keep_src[idx] != 0u)) keep_bits &= ~(1u << i);
     }
     // values are requested now so that their latency hides behind the ranking
 #pragma unroll
@@ -149,17 +159,19 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
         const uint32_t d = (key[i] >> shift) & mask;
-        uint32_t peers = 0xffffffffu;
+        const bool kept = (keep_bits >> i) & 1u;
+        uint32_t peers = keep_src != nullptr ? __ballot_sync(0xffffffffu, kept) : 0xffffffffu;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const bool bit = (d >> b) & 1u;  // (a `b < bits` guard was measured slower than the 8 fixed ballots)
             const uint32_t bal = __ballot_sync(0xffffffffu, bit);
             peers &= bit ? bal : ~bal;
         }
+        // a dropped lane keeps a peer mask without itself in it (possibly empty): it neither leads nor ranks
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
-        if (lane == leader) pre = atomicAdd(&s_warp_hist[warp][d], (uint32_t)__popc(peers));
-        pre = __shfl_sync(0xffffffffu, pre, leader);
+        if (kept && lane == leader) pre = atomicAdd(&s_warp_hist[warp][d], (uint32_t)__popc(peers));
+        pre = __shfl_sync(0xffffffffu, pre, leader < 0 ? 0 : leader);
         rank[i] = (uint16_t)(pre + __popc(peers & lt_mask));
     }
     __syncthreads();
@@ -176,9 +188,13 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     uint32_t* my_lb = lookback + (size_t)tile * 256 + tid;
     if (!precomputed_offsets) st_volatile_u32(my_lb, total | (tile == 0 ? LB_FLAG_PREFIX : LB_FLAG_AGG));
 
-    uint32_t local_start = block_exclusive_scan_256(total, s_scan);
+    uint32_t tile_kept = 0;  // items of this tile that take part (== its size unless pass-0 compaction drops some)
+    uint32_t local_start = block_exclusive_scan_256(total, s_scan, &tile_kept);
     uint32_t ghist = hist[tid];
-    uint32_t gexcl = block_exclusive_scan_256(ghist, s_scan);
+    uint32_t gtotal = 0;
+    uint32_t gexcl = block_exclusive_scan_256(ghist, s_scan, &gtotal);
+    if (n_out != nullptr && blockIdx.x == 0 && tid == 0) *n_out = gtotal;  // elements this pass writes
+    if (n_dev != nullptr && tile_base >= n) return;  // block 0 of an empty input only reports the count
 
     // decoupled look-back over preceding tiles for digit `tid`
     uint32_t excl = 0;
@@ -212,6 +228,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     // scatter keys and values into tile-sorted order in shared memory
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
+        if (!((keep_bits >> i) & 1u)) continue;
         uint32_t d = (key[i] >> shift) & mask;
         uint32_t p = s_local_start[d] + s_warp_hist[warp][d] + rank[i];
         s_keys[p] = key[i];
@@ -219,7 +236,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     }
     __syncthreads();
     // coalesced-by-run write-out: slot p of the tile goes to s_bin_base[digit] + p
-    const uint32_t valid = (n - tile_base) < (uint32_t)SORT_TILE ? (n - tile_base) : (uint32_t)SORT_TILE;
+    uint32_t valid = (n - tile_base) < (uint32_t)SORT_TILE ? (n - tile_base) : (uint32_t)SORT_TILE;
+    if (keep_src != nullptr) valid = tile_kept;
 #pragma unroll
     for (int k = 0; k < SORT_IPT; ++k) {
         uint32_t p = k * SORT_THREADS + tid;
@@ -242,11 +260,17 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
 // time (4 B per pair) to precompute the offsets is cheaper.
 __global__ void __launch_bounds__(SORT_THREADS) radix_tile_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
                                                                       int shift, int bits,
-                                                                      uint32_t* __restrict__ tile_hist /*[256][tiles]*/) {
+                                                                      uint32_t* __restrict__ tile_hist /*[256][tiles]*/,
+                                                                      const unsigned long long* __restrict__ n_dev,
+                                                                      const uint32_t* __restrict__ keep_src) {
     __shared__ uint32_t s_hist[256];
     const int tid = threadIdx.x;
     s_hist[tid] = 0;
     __syncthreads();
+    if (n_dev != nullptr) {  // device-side count: tiles past it publish zero histograms
+        const unsigned long long nd = *n_dev;
+        n = nd < n ? (uint32_t)nd : n;
+    }
     const uint32_t mask = (1u << bits) - 1u;
     const uint32_t base = blockIdx.x * SORT_TILE;
 #pragma unroll
@@ -254,12 +278,15 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_tile_hist_kernel(const uin
         const uint32_t idx = base + (i * SORT_THREADS + tid) * 4;
         if (idx + 4 <= n) {
             const uint4 v = *reinterpret_cast<const uint4*>(keys + idx);
-            atomicAdd(&s_hist[(v.x >> shift) & mask], 1u);
-            atomicAdd(&s_hist[(v.y >> shift) & mask], 1u);
-            atomicAdd(&s_hist[(v.z >> shift) & mask], 1u);
-            atomicAdd(&s_hist[(v.w >> shift) & mask], 1u);
+            uint4 kp = make_uint4(1u, 1u, 1u, 1u);
+            if (keep_src != nullptr) kp = *reinterpret_cast<const uint4*>(keep_src + idx);
+            if (kp.x) atomicAdd(&s_hist[(v.x >> shift) & mask], 1u);
+            if (kp.y) atomicAdd(&s_hist[(v.y >> shift) & mask], 1u);
+            if (kp.z) atomicAdd(&s_hist[(v.z >> shift) & mask], 1u);
+            if (kp.w) atomicAdd(&s_hist[(v.w >> shift) & mask], 1u);
         } else {
-            for (uint32_t j = idx; j < n && j < idx + 4; ++j) atomicAdd(&s_hist[(keys[j] >> shift) & mask], 1u);
+            for (uint32_t j = idx; j < n && j < idx + 4; ++j)
+                if (keep_src == nullptr || keep_src[j] != 0u) atomicAdd(&s_hist[(keys[j] >> shift) & mask], 1u);
         }
     }
     __syncthreads();
@@ -298,7 +325,12 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
                                        const char* hist_name = "sort_hist", const char* scan_name = "sort_scan",
                                        const char* pass_name = "sort_pass",
                                        bool iota_values = false, bool first_hist_ready = false,
-                                       const uint32_t* gather_src = nullptr, uint32_t* gather_dst = nullptr) {
+                                       const uint32_t* gather_src = nullptr, uint32_t* gather_dst = nullptr,
+                                       const unsigned long long* n_dev = nullptr, const uint32_t* keep_src = nullptr,
+                                       unsigned long long* n_kept_out = nullptr) {
+    // n_dev: the element count lives on the device (n is then the capacity the grids cover).  keep_src / n_kept_out:
+    // pass 0 drops every element i with keep_src[i] == 0 (stable compaction for free: later passes and the caller
+    // work on *n_kept_out elements, which later passes read from the device).
     if (n <= 0) return true;
     SortPlan plan = make_sort_plan(total_bits);
     size_t tiles = sort_num_tiles(n);
@@ -315,8 +347,9 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
         uint32_t* tile_offsets = lookback + (size_t)p * tiles * 256;
         if (!(first_hist_ready && p == 0)) {  // else the producer of the keys already filled pass 0's tile histograms
             ProfScope ps(hist_name, stream);
-            radix_tile_hist_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(ki, (uint32_t)n, plan.shift[p],
-                                                                                plan.bits[p], tile_offsets);
+            radix_tile_hist_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
+                ki, (uint32_t)n, plan.shift[p], plan.bits[p], tile_offsets, (keep_src && p > 0) ? n_kept_out : n_dev,
+                p == 0 ? keep_src : nullptr);
         }
         {
             ProfScope ps(scan_name, stream);
@@ -330,7 +363,8 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
         onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
             ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
             (iota_values && p == 0) ? 1 : 0, /*precomputed_offsets=*/1, last ? gather_src : nullptr,
-            last ? gather_dst : nullptr);
+            last ? gather_dst : nullptr, (keep_src && p > 0) ? n_kept_out : n_dev, p == 0 ? keep_src : nullptr,
+            (keep_src && p == 0) ? n_kept_out : nullptr);
         in_a = !in_a;
     }
     return in_a;

@@ -27,10 +27,10 @@ def parse_buffers(P: int, R: int, W: int, H: int, geom: torch.Tensor, binning: t
     gl, bl, il = _lib.GeomLayout(), _lib.BinningLayout(), _lib.ImageLayout()
     lib.grpg_get_geometry_layout(P, C.byref(gl))
     if P > 0:
-        counts = _view(geom, gl.num_rendered, 2, torch.int64).cpu()
-        num_rendered, R = int(counts[1]), int(counts[0])
+        counts = _view(geom, gl.num_rendered, 4, torch.int64).cpu()
+        num_rendered, R, n_sorted = int(counts[1]), int(counts[0]), int(counts[3])
     else:
-        num_rendered = R
+        num_rendered, n_sorted = R, 0
     lib.grpg_get_binning_layout(R, C.byref(bl))
     lib.grpg_get_image_layout(W, H, C.byref(il))
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
@@ -40,7 +40,9 @@ def parse_buffers(P: int, R: int, W: int, H: int, geom: torch.Tensor, binning: t
         means2D=rec[:, 0, 0:2], conic_opacity=rec[:, 1, :], rgb=rec[:, 2, 0:3],
         depths=rec[:, 2, 3], tiles_touched=_view(geom, gl.tiles_touched, P, torch.int32),
         cov3D=_view(geom, gl.cov3d, P * 6, torch.float32).view(P, 6), clamped=_view(geom, gl.clamped, P, torch.uint8),
-        sorted_idx=_view(geom, gl.sorted_idx, P, torch.int32), offsets=_view(geom, gl.offsets, P, torch.int32),
+        # depth order of the Gaussians that emit instances (tiles_touched != 0): the first n_sorted entries
+        sorted_idx=_view(geom, gl.sorted_idx, P, torch.int32)[:n_sorted],
+        offsets=_view(geom, gl.offsets, P, torch.int32)[:n_sorted],
         rect_min=torch.stack([rect[:, 0] & 0xFFFF, rect[:, 1] & 0xFFFF], 1),
         rect_max=torch.stack([(rect[:, 0] >> 16) & 0xFFFF, (rect[:, 1] >> 16) & 0xFFFF], 1),
         n_contrib=_view(img, il.n_contrib, W * H, torch.int32).view(H, W),

@@ -46,7 +46,8 @@ typedef struct grpg_geom_layout {
     size_t sorted_idx;     /* uint32[P]: Gaussian ids ordered by (depth bits, id)           */
     size_t offsets;        /* uint32[P]: exclusive scan of tiles_touched in sorted order    */
     size_t scratch;        /* sort ping-pong buffers, histograms, look-back state           */
-    size_t num_rendered;   /* uint64[2] device copies of (num_binned, num_rendered)         */
+    size_t num_rendered;   /* uint64[4] device counters: num_binned, num_rendered (the reference's), overflow flag of
+                            * the static-capacity mode, Gaussians in the depth order (those with tiles_touched != 0) */
 } grpg_geom_layout;
 
 typedef struct grpg_binning_layout {
@@ -160,6 +161,16 @@ int grpg_forward_render(const grpg_forward_args* a, int num_binned);
  * returned and the caller allocates grpg_get_binning_layout(*num_binned) bytes and calls grpg_forward_render. */
 #define GRPG_NEED_BINNING 2
 int grpg_forward(const grpg_forward_args* a, size_t binning_capacity_bytes, int* num_binned, int* num_rendered);
+
+/* The whole forward WITHOUT a host synchronisation (no reference counterpart: the reference blocks on a device-to-host
+ * copy of num_rendered, rasterizer_impl.cu:284): `a->binning_ws` holds grpg_get_binning_layout(capacity) bytes, every
+ * kernel behind the prefix sum reads the instance count from device memory and its grid covers `capacity`.  The call
+ * only enqueues work on `a->stream`, so it can be captured into a CUDA graph.  If the frame needs more than `capacity`
+ * instances the surplus is dropped (the image is then incomplete) and the overflow counter is set -- the caller must
+ * read the counters and re-render with a larger capacity: when `counts_host` (4 x uint64 of pinned host memory) is not
+ * NULL, (num_binned, num_rendered, overflow, depth-sorted Gaussians) are copied into it asynchronously on the stream.
+ * grpg_backward takes R = capacity for a forward made this way. */
+int grpg_forward_static(const grpg_forward_args* a, long long capacity, unsigned long long* counts_host);
 
 /* ------------------------------------------------------------------------- */
 /* Backward.  Replaces CudaRasterizer::Rasterizer::backward                   */
