@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1280)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph execution mode (eager launches only)")
     return ap.parse_args()
 
 
@@ -395,6 +396,74 @@ def main():
     ms_e2e_fb = time_region(e2e_fb_prefetch, args.steps, False, steps_e2e)
     ms_e2e_f = time_region(e2e_f, args.steps, False)
     ms_e2e_rgb8 = time_region(e2e_rgb8, args.steps, False)
+    # ---- the same step without any host synchronisation, as ONE CUDA graph (static binning capacity) -----------------
+    # The reference blocks on a device-to-host copy of num_rendered inside every forward (rasterizer_impl.cu:284) and so
+    # does this library's default path; `set_static_binning` moves the count to the device, which makes forward + loss +
+    # backward capturable.  Per step the host then copies the camera into the graph's input buffer, replays, and reads
+    # the loss.  Only this library's arm can do this (the reference's forward cannot be captured).
+    graph_info = None
+    if args.impl == "ours" and not args.no_graph:
+        try:
+            from gaussianrpg_b200 import _C as _gC
+            with torch.no_grad():
+                probe = fwd_only(view, proj, campos)
+            del probe
+            n_binned = max(_gC._last_binned.values())
+            capacity = int(n_binned * 1.25) + 4096
+            _gC.set_static_binning(capacity)
+            cam_s = cam_host.to(dev)
+            gt_s = gt_dev.clone()
+            gstate = {}
+
+            def gstep():
+                gstate["loss"] = fwd_bwd(cam_s[:16].view(4, 4), cam_s[16:32].view(4, 4), cam_s[32:35], gt_s)
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    gstep()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            _gC.check_static_binning()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                gstep()
+            for _ in range(3):
+                graph.replay()
+            steps_g = []
+            ms_g = time_region(graph.replay, args.steps, False, steps_g)
+            _gC.check_static_binning()
+            gi = {"i": 0}
+
+            def e2e_graph():
+                i = gi["i"]
+                gi["i"] = i + 1
+                cam_s.copy_(cam_host, non_blocking=True)
+                prefetch((i + 1) & 1)
+                if gt_evt[i & 1] is not None:
+                    torch.cuda.current_stream().wait_event(gt_evt[i & 1])
+                gt_s.copy_(gt_buf[i & 1])  # device to device: the graph reads one fixed buffer
+                graph.replay()
+                return float(gstate["loss"].item())
+
+            prefetch(0)
+            for _ in range(3):
+                e2e_graph()
+            steps_ge = []
+            ms_ge = time_region(e2e_graph, args.steps, False, steps_ge)
+            _gC.check_static_binning()
+            graph_info = {"value": 1000.0 * args.steps / ms_g, "ms_per_step": ms_g / args.steps,
+                          "ms_per_step_stats": percentiles(steps_g), "e2e_value": 1000.0 * args.steps / ms_ge,
+                          "e2e_ms_per_step": percentiles(steps_ge), "static_binning_capacity": capacity,
+                          "counts": list(_gC.static_binning_counts().values())[-1]}
+            del graph
+        except Exception as exc:  # never lose the eager numbers to a capture problem
+            graph_info = {"error": repr(exc)[:400]}
+        finally:
+            from gaussianrpg_b200 import _C as _gC
+            _gC.set_static_binning(None)
+            torch.cuda.synchronize()
     clk = clocks.stop()
 
     # scene statistics (one extra forward)
@@ -443,6 +512,19 @@ def main():
                 "timing": "CUDA events on the current stream around K steps after W warm-up steps"},
     )
 
+    if graph_info is not None:
+        result["cuda_graph"] = graph_info
+        if "error" not in graph_info:
+            # headline = the sync-free graph execution of the same step; the eager numbers stay beside it
+            result["value_eager"], result["ms_per_step_eager"] = result["value"], result["ms_per_step"]
+            result["e2e"]["value_eager"] = result["e2e"]["value"]
+            result["value"], result["ms_per_step"] = graph_info["value"], graph_info["ms_per_step"]
+            result["ms_per_step_stats"] = graph_info["ms_per_step_stats"]
+            result["e2e"]["value"] = graph_info["e2e_value"]
+            result["e2e"]["ms_per_step"] = graph_info["e2e_ms_per_step"]
+            result["execution"] = ("forward + loss + backward replayed as one CUDA graph per step (static binning capacity, "
+                                   "no host synchronisation); *_eager = the same step with eager launches and the default "
+                                   "synchronising forward")
     if args.impl == "ours":
         from gaussianrpg_b200 import _lib
         import ctypes as C

@@ -227,7 +227,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                  dL_dout_depth, dL_dout_alpha, dL_dout_semantic, sh, degree, campos, geomBuffer, R,
                                  binningBuffer, imageBuffer, alphas, semantics, debug, *, _band=(1, 0), _height=None,
                                  _width=None, _stage=3, _grad_rec=None, _slice=None, _peer_grad=None, _wanted=None,
-                                 _full_frame_grads=False):
+                                 _full_frame_grads=False, _grad_rec_rows=None, _full_rows=False):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:126-220).
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
@@ -242,7 +242,9 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     (booleans; the autograd function passes `ctx.needs_input_grad`) skips allocating and writing the outputs nobody
     reads -- they come back as None -- as well as the two internal ones (dL_dconic, dL_ddepth).
     `_full_frame_grads=True` (with a band): the four pixel-gradient images are full frames [C,H,W], read by the kernel
-    at the band's true rows, instead of compact band images.
+    at the band's true rows, instead of compact band images.  `_grad_rec_rows` (stage 1): allocate the record buffer
+    with that many rows (>= P, the surplus zeroed) so that it can be reduce-scattered without a padding copy.
+    `_full_rows=True` (stage 2 on a slice): the gradients come back with all P rows, zero outside the slice.
     """
     _require_cuda()
     lib = _lib.load()
@@ -262,10 +264,17 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     M = int(sh.shape[1]) if sh is not None and sh.numel() != 0 else 0
     f32 = dict(dtype=torch.float32, device=dev)
     p_begin, p_count = (0, P) if _slice is None else (int(_slice[0]), int(_slice[1]))
-    Pout = P if _stage != 2 else p_count
+    full_rows = bool(_full_rows) and _stage == 2 and (p_begin != 0 or p_count != P)
+    Pout = P if (_stage != 2 or full_rows) else p_count
+    row0 = p_begin if full_rows else 0  # the kernel writes rows [0, p_count) behind the pointers it is given
 
-    def out(*shape):  # fully written by grpg_backward
-        return torch.empty(shape, **f32) if P != 0 else torch.zeros(shape, **f32)
+    def out(*shape):  # fully written by grpg_backward (a slice of a full-row result: zero elsewhere)
+        return torch.zeros(shape, **f32) if (P == 0 or full_rows) else torch.empty(shape, **f32)
+
+    def at(t):  # device pointer of row `row0`
+        if t is None or t.numel() == 0:
+            return None
+        return t.data_ptr() + row0 * t.stride(0) * 4
 
     if _stage == 1:
         Pout = 0  # no per-parameter outputs in the blend-only stage
@@ -309,14 +318,17 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     a.geom_ws, a.binning_ws, a.image_ws = _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer)
     a.dL_dpix, a.dL_dpix_depth = _ptr(opt(dL_dout_color)), _ptr(opt(dL_dout_depth))
     a.dL_dalphas, a.dL_dpix_semantic = _ptr(opt(dL_dout_alpha)), _ptr(opt(dL_dout_semantic))
-    a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = _ptr(dL_dmeans2D), _ptr(dL_dconic), dL_dopacity.data_ptr()
-    a.dL_dcolor, a.dL_ddepth, a.dL_dmean3D = _ptr(dL_dcolors), _ptr(dL_ddepths), dL_dmeans3D.data_ptr()
-    a.dL_dcov3D, a.dL_dsh = _ptr(dL_dcov3D), _ptr(dL_dsh)
-    a.dL_dscale, a.dL_drot, a.dL_dsemantic = _ptr(dL_dscales), _ptr(dL_drot), _ptr(dL_dsemantic)
+    a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = at(dL_dmeans2D), at(dL_dconic), at(dL_dopacity)
+    a.dL_dcolor, a.dL_ddepth, a.dL_dmean3D = at(dL_dcolors), at(dL_ddepths), at(dL_dmeans3D)
+    a.dL_dcov3D, a.dL_dsh = at(dL_dcov3D), at(dL_dsh)
+    a.dL_dscale, a.dL_drot, a.dL_dsemantic = at(dL_dscales), at(dL_drot), _ptr(dL_dsemantic)
     if _grad_rec is not None:
         grad_ws = _grad_rec.contiguous()
     else:
-        grad_ws = torch.empty((P, 12), dtype=torch.float32, device=dev)
+        rows = max(P, int(_grad_rec_rows or 0))
+        grad_ws = torch.empty((rows, 12), dtype=torch.float32, device=dev)
+        if rows > P:
+            grad_ws[P:].zero_()
     a.grad_ws = grad_ws.data_ptr()
     a.stream = _stream(dev)
     a.tile_row_stride, a.tile_row_phase = stride, phase

@@ -104,20 +104,33 @@ def _all_gather_rows(x: torch.Tensor, group, k: int) -> torch.Tensor:
     return out
 
 
-_EXCHANGE_PLAN = "replicate"  # or "shard"; see _ShardedRasterize.backward
+_native = None  # the `_C`-style module the sharded operator drives (tests inject a CPU stand-in)
+
+
+def _C_module():
+    if _native is not None:
+        return _native
+    from . import _C
+    return _C
 
 
 class _PeerFrame:
-    """Peer-mapped full-frame output buffer (torch symmetric memory over NVLink).  With it the blend kernel of every
-    rank stores its band's pixels directly into all ranks' frames -- the forward all-gather becomes the kernel's
-    epilogue (peer stores) instead of a separate NCCL collective plus an interleave copy."""
+    """Peer-mapped full-frame output buffers (torch symmetric memory over NVLink).  With them the blend kernel of every
+    rank stores its band's pixels directly into all ranks' frames -- the forward all-gather is the kernel's epilogue
+    (peer stores) instead of a separate NCCL collective plus an interleave copy.  Two buffers alternate between calls:
+    a rank can only pass the barrier that closes call i+1 after every rank has enqueued, in stream order, everything
+    that reads the frame of call i, so call i+2 may overwrite that buffer without a second barrier and the operator can
+    hand out views of the buffers themselves (no copy)."""
     _cache = {}
 
     def __init__(self, channels: int, H: int, W: int, device, group):
         import torch.distributed._symmetric_memory as symm_mem
-        self.frame = symm_mem.empty((channels, H, W), dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.frame, group)
-        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.frames, self.handles, self.ptrs = [], [], []
+        for _ in range(2):
+            f = symm_mem.empty((channels, H, W), dtype=torch.float32, device=device)
+            h = symm_mem.rendezvous(f, group)
+            self.frames.append(f); self.handles.append(h); self.ptrs.append([int(p) for p in h.buffer_ptrs])
+        self.turn = 0
 
     @classmethod
     def get(cls, channels, H, W, device, group):
@@ -132,77 +145,74 @@ class _PeerFrame:
         return cls._cache[key]
 
 
-class _PeerRecords:
-    """Peer-mapped [P,12] gradient-record buffer: every rank's blend backward accumulates into its own copy, and
-    the per-Gaussian backward of every rank sums all copies in its load path (no separate all-reduce)."""
-    _cache = {}
-
-    def __init__(self, P: int, device, group):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.rec = symm_mem.empty((P, 12), dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.rec, group)
-        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
-
-    @classmethod
-    def get(cls, P, device, group):
-        key = (P, str(device), id(group))
-        if key not in cls._cache:
-            try:
-                cls._cache[key] = cls(P, device, group)
-            except Exception as exc:
-                cls._cache[key] = None
-                if dist.get_rank(group) == 0:
-                    print(f"[gaussianrpg_b200.dist] symmetric memory unavailable ({exc!r}); using NCCL all-reduce")
-        return cls._cache[key]
-
-
 FUSED_FORWARD_GATHER = True  # set False to force the NCCL all-gather path
-# Sum the gradient records inside the per-Gaussian backward (peer loads) for groups up to this size.  Reading
-# k-1 peers directly costs (k-1) x 48 B per visible Gaussian against 2(k-1)/k x 48 B per Gaussian for the ring
-# all-reduce, so the direct form only wins (fewer bytes, one kernel less, no extra pass over HBM) for small k.
-FUSED_RECORD_REDUCE_MAX_RANKS = 0
+
+
+def _forward_band(rs, tensors, k, r, peer_ptrs=None, forward_only=False):
+    (means3D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp) = tensors
+    return _C_module().rasterize_gaussians(rs.bg, means3D, colors_precomp, semantics, opacities, scales, rotations,
+                                           rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx,
+                                           rs.tanfovy, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos,
+                                           rs.prefiltered, rs.debug, _band=(k, r), _peer_frames=peer_ptrs,
+                                           _forward_only=forward_only)
 
 
 # ---- the sharded operator --------------------------------------------------------------------------
 class _ShardedRasterize(torch.autograd.Function):
+    """One frame split over the ranks of `group` by interleaved tile rows.
+
+    output    "frame": every rank receives the whole frame (forward exchange: fused peer-store epilogue of the blend
+              kernel, or an NCCL all-gather); the pixel gradients it gets back are full frames of which it reads its rows.
+              "band":  the rank keeps its own rows only ([C, band_rows*16, W], see `frame_to_band`); nothing is
+              exchanged in the forward -- a training step evaluates its loss on the band.
+    gradients "full":  the 48-byte per-Gaussian 2D gradient records are all-reduced and every rank runs the
+              per-Gaussian backward for all Gaussians (every rank returns the complete gradients).
+              "shard": the records are reduce-scattered over the Gaussian axis, rank r runs the per-Gaussian backward
+              for its slice `gaussian_slice(P, k, r)` only and returns gradients that are complete on that slice and
+              zero elsewhere (the sum over ranks is the complete gradient; a sharded optimiser uses the slice as is).
+    """
+
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, group):
-        from . import _C
+                raster_settings, group, output, gradients, grad_mode):
         rs = raster_settings
         k, r = dist.get_world_size(group), dist.get_rank(group)
         H, W = rs.image_height, rs.image_width
         S_in = int(semantics.shape[1]) if semantics is not None and semantics.ndim == 2 else 0
+        fwd_only = (not grad_mode) or not any(ctx.needs_input_grad)
+        tensors = (means3D, sh, colors_precomp, semantics, opacities, scales, rotations, cov3Ds_precomp)
         peer = None
-        if FUSED_FORWARD_GATHER and k > 1 and k <= 8 and means3D.is_cuda and dist.get_backend(group) == "nccl":
+        if (output == "frame" and FUSED_FORWARD_GATHER and 1 < k <= 8 and means3D.is_cuda
+                and dist.get_backend(group) == "nccl"):
             peer = _PeerFrame.get(5 + S_in, H, W, means3D.device, group)
+        turn = 0
         if peer is not None:
-            peer.handle.barrier(channel=0)  # every rank has finished reading the previous frame
-        out = _C.rasterize_gaussians(rs.bg, means3D, colors_precomp, semantics, opacities, scales, rotations,
-                                     rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx,
-                                     rs.tanfovy, H, W, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug,
-                                     _band=(k, r), _peer_frames=peer.ptrs if peer is not None else None)
+            turn = peer.turn
+            peer.turn ^= 1
+        out = _forward_band(rs, tensors, k, r, peer.ptrs[turn] if peer is not None else None, fwd_only)
         R, color_b, depth_b, alpha_b, sem_b, radii, geom, binning, img = out
         S = sem_b.shape[0]
-        if peer is not None:
-            peer.handle.barrier(channel=1)  # every rank's band has landed in this rank's frame
-            frame = peer.frame.clone()
+        if output == "band":
+            color, depth, alpha, sem = color_b, depth_b, alpha_b, sem_b
+        elif peer is not None:
+            peer.handles[turn].barrier(channel=0)  # every rank's band has landed in this rank's frame
+            frame = peer.frames[turn]
+            color, depth, alpha, sem = frame[:3], frame[3:4], frame[4:5], frame[5:5 + S]
         else:
             packed = pad_band(torch.cat([color_b, depth_b, alpha_b, sem_b], 0), H, k)  # one collective for all planes
-            gathered = _all_gather_rows(packed[None], group, k)
-            frame = bands_to_frame(gathered, H)
-        color, depth, alpha, sem = frame[:3], frame[3:4], frame[4:5], frame[5:5 + S]
-        ctx.rs, ctx.group, ctx.R = rs, group, R
+            frame = bands_to_frame(_all_gather_rows(packed[None], group, k), H)
+            color, depth, alpha, sem = frame[:3], frame[3:4], frame[4:5], frame[5:5 + S]
+        ctx.rs, ctx.group, ctx.R, ctx.output, ctx.gradients = rs, group, R, output, gradients
         ctx.tensor_inputs = [isinstance(t, torch.Tensor) for t in (means3D, means2D, sh, colors_precomp, semantics,
                                                                    opacities, scales, rotations, cov3Ds_precomp)]
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning,
                               img, alpha_b, semantics)
         ctx.mark_non_differentiable(radii)
-        return color.contiguous(), radii, depth.contiguous(), alpha.contiguous(), sem.contiguous()
+        return color, radii, depth, alpha, sem
 
     @staticmethod
     def backward(ctx, g_color, g_radii, g_depth, g_alpha, g_sem):
-        from . import _C
+        C_ = _C_module()
         rs, group = ctx.rs, ctx.group
         k, r = dist.get_world_size(group), dist.get_rank(group)
         (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img, alpha_b,
@@ -210,68 +220,47 @@ class _ShardedRasterize(torch.autograd.Function):
         H, W = rs.image_height, rs.image_width
         P = means3D.shape[0]
         S = g_sem.shape[0]
-        # the blend backward reads the band's rows straight out of the full-frame loss gradients
         common = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                   rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy)
         tail = (sh, rs.sh_degree, rs.campos, geom, ctx.R, binning, img, alpha_b, semantics, rs.debug)
-        peer_rec = None
-        if (_EXCHANGE_PLAN == "replicate" and 1 < k <= FUSED_RECORD_REDUCE_MAX_RANKS and means3D.is_cuda
-                and dist.get_backend(group) == "nccl"):
-            peer_rec = _PeerRecords.get(P, means3D.device, group)
-        grad_rec, g_semantics = _C.rasterize_gaussians_backward(
+        # "frame": the blend backward reads the band's rows straight out of the full-frame loss gradients
+        grad_rec, g_semantics = C_.rasterize_gaussians_backward(
             *common, g_color.contiguous(), g_depth.contiguous(), g_alpha.contiguous(), g_sem.contiguous(), *tail,
-            _band=(k, r), _height=H, _width=W, _stage=1, _full_frame_grads=True,
-            _grad_rec=peer_rec.rec if peer_rec is not None else None)
-        # Sum the per-Gaussian 2D gradient records over ranks.  Two exchange plans:
-        #  "shard":     reduce-scatter the 48 B records, per-Gaussian backward on the owned slice, all-gather the
-        #               parameter-gradient shards (104 B per Gaussian for means/sh/opacity/scale/rotation);
-        #  "replicate": reduce-scatter + all-gather of the 48 B records themselves (= all-reduce), then every rank
-        #               runs the (cheap, 0.15 ms at 2 M) per-Gaussian backward for all Gaussians.
-        # "replicate" moves less than half the bytes and is the default; "shard" is what a ZeRO-style sharded
-        # optimiser would use (it would simply skip the final all-gather).
-        if _EXCHANGE_PLAN == "replicate":
-            if peer_rec is not None:
-                peer_rec.handle.barrier(channel=2)  # every rank's records are complete
-            else:
-                dist.all_reduce(grad_rec, op=dist.ReduceOp.SUM, group=group)
-            shard = _C.rasterize_gaussians_backward(
+            _band=(k, r), _height=H, _width=W, _stage=1, _full_frame_grads=(ctx.output == "frame"),
+            _grad_rec_rows=padded_count(P, k))
+        need = ctx.needs_input_grad
+        wanted = (need[1], need[3], need[8], need[6] or need[7])
+        if ctx.gradients == "full":
+            dist.all_reduce(grad_rec, op=dist.ReduceOp.SUM, group=group)
+            shard = C_.rasterize_gaussians_backward(
                 *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _width=W, _stage=2,
-                _grad_rec=grad_rec, _slice=(0, P), _peer_grad=peer_rec.ptrs if peer_rec is not None else None)
-            if peer_rec is not None:
-                peer_rec.handle.barrier(channel=3)  # nobody still reads this rank's records: they may be reused
-            g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = shard[:8]
+                _grad_rec=grad_rec, _slice=(0, P), _wanted=wanted)
         else:
-            Pp = padded_count(P, k)
-            if Pp != P:
-                grad_rec = torch.nn.functional.pad(grad_rec, (0, 0, 0, Pp - P))
-            mine = _reduce_scatter_rows(grad_rec, group, k, r)
+            mine = _reduce_scatter_rows(grad_rec, group, k, r)  # grad_rec has padded_count(P, k) rows
             p_begin, p_count = gaussian_slice(P, k, r)
-            shard = _C.rasterize_gaussians_backward(
+            shard = C_.rasterize_gaussians_backward(
                 *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _width=W, _stage=2,
-                _grad_rec=mine[:max(p_count, 1)], _slice=(p_begin, p_count))
-            per = Pp // k
-            full = []
-            for t in shard[:8]:  # means2D, colors, opacity, means3D, cov3D, sh, scales, rot
-                flat = t.reshape(t.shape[0], -1)
-                if flat.shape[0] != per:
-                    flat = torch.nn.functional.pad(flat, (0, 0, 0, per - flat.shape[0]))
-                g = _all_gather_rows(flat, group, k)[:P]
-                full.append(g.reshape((P,) + tuple(t.shape[1:])))
-            g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = full
+                _grad_rec=mine, _slice=(p_begin, p_count), _wanted=wanted, _full_rows=True)
+        g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot = shard[:8]
         if S > 0:
             dist.all_reduce(g_semantics, op=dist.ReduceOp.SUM, group=group)
         grads = (g_means3D, g_means2D, g_sh, g_colors, g_semantics, g_opac, g_scales, g_rot, g_cov3D)
-        return tuple(g if is_t else None for g, is_t in zip(grads, ctx.tensor_inputs)) + (None, None)
+        return tuple(g if is_t else None for g, is_t in zip(grads, ctx.tensor_inputs)) + (None,) * 5
 
 
 class ShardedGaussianRasterizer(nn.Module):
-    """Drop-in for `GaussianRasterizer` when every rank of `group` holds the same Gaussians and camera:
-    same arguments, same 5-tuple, same (full) gradients on every rank."""
+    """`GaussianRasterizer` for one frame split over the ranks of `group`, every rank holding the same Gaussians and
+    camera: same arguments, same 5-tuple.  Defaults (`output="frame"`, `gradients="full"`) make it a drop-in: the whole
+    frame and the complete gradients on every rank.  A data-parallel training step uses `output="band"` (the rank's own
+    rows; slice the ground truth with `frame_to_band`) and `gradients="shard"` (see `_ShardedRasterize`)."""
 
-    def __init__(self, raster_settings, group=None):
+    def __init__(self, raster_settings, group=None, output: str = "frame", gradients: str = "full"):
         super().__init__()
+        if output not in ("frame", "band") or gradients not in ("full", "shard"):
+            raise ValueError("output must be 'frame' or 'band', gradients 'full' or 'shard'")
         self.raster_settings = raster_settings
         self.group = group if group is not None else dist.group.WORLD
+        self.output, self.gradients = output, gradients
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None, semantics=None):
@@ -286,115 +275,308 @@ class ShardedGaussianRasterizer(nn.Module):
         return _ShardedRasterize.apply(means3D, means2D, E if shs is None else shs,
                                        E if colors_precomp is None else colors_precomp, semantics, opacities,
                                        E if scales is None else scales, E if rotations is None else rotations,
-                                       E if cov3D_precomp is None else cov3D_precomp, self.raster_settings, self.group)
+                                       E if cov3D_precomp is None else cov3D_precomp, self.raster_settings, self.group,
+                                       self.output, self.gradients, torch.is_grad_enabled())
 
 
 # ---- bench.py --gpus N ------------------------------------------------------------------------------
+def _profile_kernels(fn, reps=3):
+    """per-kernel CUDA-event times of this rank's library launches during `fn` (grpg_profile_begin/end)"""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    lib.grpg_profile_begin()
+    for _ in range(reps):
+        fn()
+    buf = C.create_string_buffer(8192)
+    lib.grpg_profile_end(buf, 8192)
+    kern = {}
+    for line in buf.value.decode().strip().splitlines():
+        n, c, ms = line.split(":")
+        kern[n] = {"launches_per_step": int(c) // reps, "ms_per_step": float(ms) / reps}
+    return kern
+
+
 def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
-    """One frame of the 2 M-Gaussian scene split over `world` GPUs (strong scaling): forward + backward with the
-    collectives inside the timed region, device-timed, max over ranks."""
+    """One frame of the 2 M-Gaussian scene split over `world` GPUs (strong scaling).
+
+    Training step (the `value`): every rank renders its interleaved tile rows, evaluates the loss on those rows
+    (ground truth and weights sliced once with `frame_to_band`), replays its rows in the blend backward, the 48-byte
+    per-Gaussian records are reduce-scattered (NCCL) and the per-Gaussian backward runs on the rank's slice of the
+    Gaussians -- gradient shards, as a sharded optimiser consumes them.  No forward collective is needed for a training
+    step.  The step runs without a host synchronisation (static binning capacity) and, when the capture succeeds, as
+    ONE CUDA graph per rank (all kernels + the reduce-scatter).  Forward-only fps (BASELINE config #5) = band render +
+    fused peer-store all-gather of the frame.  Device-timed, max over ranks."""
+    import json
+    import time
+    from pathlib import Path
+    from . import _C
+    from .rasterizer import GaussianRasterizer
     sc = sc_cpu.to(dev)
     H, W = sc.height, sc.width
+    P = sc.means3D.shape[0]
     g = torch.Generator().manual_seed(123)
     gt = torch.rand(3, H, W, generator=g).to(dev)
     w_depth = (torch.rand(1, H, W, generator=g) * 0.01).to(dev)
     w_alpha = (torch.rand(1, H, W, generator=g) * 0.1).to(dev)
+    gt_b, wd_b, wa_b = (frame_to_band(t, world, rank) for t in (gt, w_depth, w_alpha))
+    n_pix = float(H * W)
     leaves = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
-    rast = ShardedGaussianRasterizer(sc.settings())
-    P = sc.means3D.shape[0]
+    means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
+    rast_train = ShardedGaussianRasterizer(sc.settings(), output="band", gradients="shard")
+    rast_frame = ShardedGaussianRasterizer(sc.settings(), output="frame", gradients="full")
+    kw = lambda: dict(means3D=leaves["means3D"], opacities=leaves["opacities"], shs=leaves["shs"],  # noqa: E731
+                      scales=leaves["scales"], rotations=leaves["rotations"])
+    HLb = gt_b.shape[1]
+    hb = min(HLb, max(0, H))  # band rows inside the frame (the last tile row of a ragged frame is padded)
 
-    def fwd_bwd():
+    def band_loss(color, depth, alpha, gt_band):
+        # the rank's share of the full-frame means: sums over its rows divided by the frame's pixel count
+        return ((color - gt_band).abs().sum() / (3 * n_pix) + (depth * wd_b).sum() / n_pix + (alpha * wa_b).sum() / n_pix)
+
+    state = {}
+
+    def train_step(gt_band=gt_b):
         for v in leaves.values():
             v.grad = None
-        means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
-        color, radii, depth, alpha, _ = rast(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
-                                             shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
-        loss = (color - gt).abs().mean() + (depth * w_depth).mean() + (alpha * w_alpha).mean()
+        means2D.grad = None
+        color, radii, depth, alpha, _ = rast_train(means2D=means2D, **kw())
+        loss = band_loss(color, depth, alpha, gt_band)
         loss.backward()
+        state["loss"] = loss
         return loss
 
     def fwd_only():
         with torch.no_grad():
-            return rast(means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"], shs=leaves["shs"],
-                        scales=leaves["scales"], rotations=leaves["rotations"])
+            return rast_frame(means2D=None, **kw())
 
-    def timed(fn, steps):
+    def timed(fn, steps, per_step=None):
         dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            ev[i + 1].record()
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if per_step is not None:
+            per_step.extend(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+        t = torch.tensor([ev[0].elapsed_time(ev[steps])], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(3, args.warmup)):
-        fwd_bwd()
-    ms_fb = timed(fwd_bwd, args.steps)
-    for _ in range(3):
-        fwd_only()
-    ms_f = timed(fwd_only, args.steps)
+    # ---- parity of the sharded step against the single-GPU operator, in-run, before anything is timed ---------------
+    solo = GaussianRasterizer(sc.settings())
+    for v in leaves.values():
+        v.grad = None
+    m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+    color, radii, depth, alpha, _ = solo(means2D=m2, **kw())
+    ((color - gt).abs().mean() + (depth * w_depth).mean() + (alpha * w_alpha).mean()).backward()
+    want = {k: v.grad.clone() for k, v in leaves.items()}
+    want["means2D"] = m2.grad.clone()
+    frame_want = torch.cat([color, depth, alpha], 0).detach()
+    train_step()
+    got = {k: v.grad.clone() for k, v in leaves.items()}
+    got["means2D"] = means2D.grad.clone()
+    p_begin, p_count = gaussian_slice(P, world, rank)
+    parity = {"grad_shard_max_rel": {}, "grad_outside_shard_nonzero": 0}
+    for k_ in got:
+        a, b = got[k_][p_begin:p_begin + p_count], want[k_][p_begin:p_begin + p_count]
+        parity["grad_shard_max_rel"][k_] = float((a - b).abs().max() / want[k_].abs().max().clamp_min(1e-30)) if p_count else 0.0
+        outside = torch.cat([got[k_][:p_begin].reshape(-1), got[k_][p_begin + p_count:].reshape(-1)])
+        parity["grad_outside_shard_nonzero"] += int((outside != 0).sum())
+    frame = fwd_only()
+    frame_got = torch.cat([frame[0], frame[2], frame[3]], 0)
+    parity["frame_differing_floats"] = int((frame_got != frame_want).sum())
+    parity["radii_mismatches"] = int((frame[1] != radii).sum())
+    worst = torch.tensor([max(parity["grad_shard_max_rel"].values()), float(parity["frame_differing_floats"]),
+                          float(parity["grad_outside_shard_nonzero"])], device=dev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    parity.update(worst_over_ranks={"grad_shard_max_rel": float(worst[0]), "frame_differing_floats": int(worst[1]),
+                                    "grad_outside_shard_nonzero": int(worst[2])},
+                  vs="single-GPU operator of this library on the same inputs (itself bit-identical in the images to the "
+                     "reference extension, bench.py parity at N=1)")
+    del want, got, frame_want, frame_got, m2, color, depth, alpha, frame
 
-    # end to end: per-step host inputs (camera + ground truth, pinned) in, loss scalar out
-    gt_host = gt.cpu().pin_memory()
+    # ---- per-kernel view and collective time of one eager step (not the timed path) -----------------------------------
+    for _ in range(2):
+        train_step()
+    kern = _profile_kernels(train_step)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    rec = torch.zeros(padded_count(P, world), 12, device=dev)
+    outb = torch.empty(padded_count(P, world) // world, 12, device=dev)
+    for _ in range(3):
+        dist.reduce_scatter_tensor(outb, rec)
+    dist.barrier(); torch.cuda.synchronize()
+    e[0].record()
+    for _ in range(5):
+        dist.reduce_scatter_tensor(outb, rec)
+    e[1].record(); torch.cuda.synchronize()
+    rs_ms = e[0].elapsed_time(e[1]) / 5
+    del rec, outb
+
+    # ---- the timed training step: sync-free, captured into one CUDA graph per rank when possible ----------------------
+    counts = _C.static_binning_counts()
+    band_parsed_R = None
+    with torch.no_grad():
+        raw = _forward_band(sc.settings(), (leaves["means3D"], leaves["shs"], torch.Tensor([]),
+                                            torch.zeros(P, 0, device=dev), leaves["opacities"], leaves["scales"],
+                                            leaves["rotations"], torch.Tensor([])), world, rank)
+        from . import debug as _dbg
+        _p = _dbg.parse_buffers(P, raw[0], W, raw[1].shape[1], raw[6], raw[7], raw[8])
+        band_parsed_R, band_R_ref = _p["num_binned"], raw[0]
+        band_V = int((_p["tiles_touched"] != 0).sum())
+        del raw, _p
+    capacity = int(band_parsed_R * 1.25) + 4096
+    _C.set_static_binning(capacity)
+    graph, graph_note = None, "eager (CUDA-graph capture not attempted)"
+    for _ in range(3):
+        train_step()
+    torch.cuda.synchronize()
+    _C.check_static_binning()
+    if not getattr(args, "no_graph", False):
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    train_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            dist.barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                train_step()
+            graph.replay()
+            torch.cuda.synchronize()
+            _C.check_static_binning()
+            graph_note = "one CUDA graph per rank: every kernel of forward + loss + backward and the NCCL reduce-scatter"
+        except Exception as exc:  # capture of the collective is the fragile part: fall back to eager launches
+            graph = None
+            graph_note = f"eager (graph capture failed: {exc!r})"[:300]
+            torch.cuda.synchronize()
+    step_fn = graph.replay if graph is not None else train_step
+    for _ in range(max(3, args.warmup)):
+        step_fn()
+    per_step = []
+    ms_fb = timed(step_fn, args.steps, per_step)
+    _C.check_static_binning()
+
+    # end to end: per-step host inputs (this rank's rows of the ground truth, pinned, one step ahead) in, loss out
+    gt_host = gt_b.cpu().pin_memory()
+    gt_slots = [gt_b.clone(), gt_b.clone()]
+    slot_ready = [None, None]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ii = {"i": 0}
+
+    def prefetch(slot):
+        copy_stream.wait_stream(torch.cuda.current_stream())  # the slot's previous reader has been enqueued
+        with torch.cuda.stream(copy_stream):
+            gt_slots[slot].copy_(gt_host, non_blocking=True)
+            slot_ready[slot] = copy_stream.record_event()
 
     def e2e():
-        gt_d = gt_host.to(dev, non_blocking=True)
-        for v in leaves.values():
-            v.grad = None
-        means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
-        color, radii, depth, alpha, _ = rast(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
-                                             shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
-        loss = (color - gt_d).abs().mean() + (depth * w_depth).mean() + (alpha * w_alpha).mean()
-        loss.backward()
-        return float(loss.item())
+        i = ii["i"]; ii["i"] = i + 1
+        cur = i & 1
+        prefetch(cur ^ 1)  # next step's image, uploaded underneath this step
+        if slot_ready[cur] is not None:
+            torch.cuda.current_stream().wait_event(slot_ready[cur])
+        if graph is not None:  # the graph reads gt_b: this step's image is copied into it (device to device, 1/N frame)
+            gt_b.copy_(gt_slots[cur])
+            graph.replay()
+            return float(state["loss"].item())
+        return float(train_step(gt_slots[cur]).item())
 
-    for _ in range(2):
+    prefetch(0)
+    for _ in range(3):
         e2e()
     ms_e2e = timed(e2e, args.steps)
+    _C.check_static_binning()
+
+    # forward-only (BASELINE config #5): band render + fused frame all-gather, eager launches, static capacity
+    for _ in range(3):
+        fwd_only()
+    steps_f = []
+    ms_f = timed(fwd_only, args.steps, steps_f)
+    _C.check_static_binning()
+    _C.set_static_binning(None)
+
     # camera-parallel companion line (SURVEY 8e: "pure camera-parallel ... should be reported beside it"): every rank
-    # renders its OWN camera of a batch of `world` cameras with the single-GPU operator, no exchange at all
-    from .rasterizer import GaussianRasterizer
-    solo = GaussianRasterizer(sc.settings())
+    # renders ITS OWN camera of a batch of `world` cameras (poses 1 m apart along the street) with the single-GPU
+    # operator, no exchange at all
+    from . import synthetic
+    cam = synthetic.street_scene(P=64, W=W, H=H, cam_z=float(rank))  # only the camera of this pose is used
+    my_settings = sc.settings()._replace(viewmatrix=cam.viewmatrix.to(dev), projmatrix=cam.projmatrix.to(dev),
+                                         campos=cam.campos.to(dev))
+    solo_cam = GaussianRasterizer(my_settings)
 
     def solo_fwd_bwd():
         for v in leaves.values():
             v.grad = None
-        means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
-        color, radii, depth, alpha, _ = solo(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
-                                             shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+        m2_ = torch.zeros(P, 3, device=dev, requires_grad=True)
+        color, radii, depth, alpha, _ = solo_cam(means2D=m2_, **kw())
         ((color - gt).abs().mean() + (depth * w_depth).mean() + (alpha * w_alpha).mean()).backward()
 
     def solo_fwd():
         with torch.no_grad():
-            solo(means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"], shs=leaves["shs"],
-                 scales=leaves["scales"], rotations=leaves["rotations"])
+            solo_cam(means2D=None, **kw())
 
     for _ in range(3):
         solo_fwd_bwd(); solo_fwd()
     ms_solo_fb = timed(solo_fwd_bwd, args.steps)
     ms_solo_f = timed(solo_fwd, args.steps)
+
+    # roofline of the dominant kernel of this rank's step (algorithmic bytes of ITS share of the frame, SURVEY 8d)
+    peaks = {}
+    try:
+        peaks = json.load(open(Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json"))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    tiles_band = ((W + 15) // 16) * band_rows(H, world, rank)
+    pix_band = W * HLb
+    alg = {"blend_bwd": 44 * band_R_ref + 28 * pix_band + 48 * band_V, "blend_fwd": 44 * band_R_ref + 8 * tiles_band + 24 * pix_band,
+           "preprocess_fwd": 44 * P + 48 * band_V + 8 * P + 67 * band_V, "preprocess_bwd": (115 + 48 + 64 + 48) * (band_V // max(1, world)),
+           "depth_sort_pass": 16 * P, "tile_sort_pass": 16 * band_parsed_R}
+    dom = max((k_ for k_ in kern if k_ in alg), key=lambda k_: kern[k_]["ms_per_step"])
+    per_launch = kern[dom]["ms_per_step"] / max(1, kern[dom]["launches_per_step"])
+    ach = alg[dom] / (per_launch * 1e-3) / 1e9
+    lib_ms = sum(v["ms_per_step"] for v in kern.values())
+    launches = sum(v["launches_per_step"] for v in kern.values())
+    xs = sorted(per_step)
+    q = lambda f: xs[min(len(xs) - 1, max(0, int(round(f * (len(xs) - 1)))))]  # noqa: E731
     band_bytes = 5 * max_band_rows(H, world) * TILE * W * 4
     return {
         "metric": "iters_per_sec_fwd_bwd_1920x1280_2M", "value": 1000.0 * args.steps / ms_fb, "unit": "iters/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_fb / args.steps,
+        "ms_per_step_stats": {"median": q(0.5), "p10": q(0.1), "p90": q(0.9), "n": len(xs), "rank": rank},
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "impl": "ours", "fwd_fps": 1000.0 * args.steps / ms_f,
-        "e2e": {"value": 1000.0 * args.steps / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": int(gt_host.numel() * 4),
-                "d2h_bytes_per_step": 4},
-        # kernels of this library per step and rank: 22 forward (preprocess, 12 depth-sort, scan, emit, 5 tile-sort,
-        # ranges, blend) + 2 backward -- the count bench.py measures with the library's profiler on one GPU
-        "gpu_launches": 24 * args.steps * world,
+        "impl": "ours", "fwd_fps": 1000.0 * args.steps / ms_f, "fwd_ms": ms_f / args.steps,
+        "e2e": {"value": 1000.0 * args.steps / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": int(gt_host.numel() * 4 * world),
+                "d2h_bytes_per_step": 4 * world,
+                "note": "per step and rank: its rows of the ground-truth image H2D from pinned memory (one step ahead, "
+                        "copy stream), its share of the loss D2H; bytes are totals over the ranks"},
+        "gpu_launches": launches * args.steps * world,
+        "execution": graph_note,
+        "kernels": kern, "kernels_note": f"rank {rank}, CUDA events around every library launch of one eager step",
+        "library_ms_per_step_rank0": lib_ms,
+        "collectives": {"reduce_scatter_records_ms": rs_ms, "bytes_per_rank_in": 48 * padded_count(P, world),
+                        "note": "NCCL reduce-scatter of the [P,12] float record buffer timed alone (5 calls, CUDA events); inside "
+                                "the step it is one node of the graph"},
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                     "algorithmic_bytes_per_launch": alg[dom],
+                     "note": f"rank {rank}'s share: R_band={band_R_ref} instances ({band_parsed_R} binned), V_band={band_V}"},
+        "parity": parity,
         "camera_parallel": {"value": 1000.0 * args.steps * world / ms_solo_fb, "unit": "iters/s",
                             "fwd_fps": 1000.0 * args.steps * world / ms_solo_f, "scaling": "weak",
-                            "note": f"a batch of {world} cameras, one per GPU, single-GPU operator, no exchange "
-                                    f"(the upper bound SURVEY 8e asks to report beside the sharded number)"},
+                            "note": f"a batch of {world} cameras (poses 1 m apart), one per GPU, single-GPU operator, no "
+                                    f"exchange (the upper bound SURVEY 8e asks to report beside the sharded number)"},
         "config": {"workload": f"street scene {P} Gaussians, {W}x{H}, fwd+bwd, one frame split over {world} GPUs",
-                   "parallelism": f"tile rows interleaved mod {world} (fwd, all-gather {band_bytes} B/rank) + "
-                                  f"all-reduce (reduce-scatter + all-gather) of the 48 B per-Gaussian gradient records "
-                                  f"(bwd, {48 * P} B), per-Gaussian backward replicated",
-                   "l2": "no flush: one step streams > 126 MB per GPU"},
+                   "parallelism": f"tile rows interleaved mod {world}; training step: loss on the rank's rows, NCCL "
+                                  f"reduce-scatter of the 48 B per-Gaussian gradient records ({48 * P} B), per-Gaussian "
+                                  f"backward on the rank's P/{world} slice (gradient shards); forward-only: fused peer-store "
+                                  f"all-gather of the frame ({band_bytes} B per rank)",
+                   "static_binning_capacity": capacity,
+                   "l2": "no flush: one step streams > 126 MB per GPU (record table 96 MB + instance lists + images)"},
     }
