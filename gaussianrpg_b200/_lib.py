@@ -106,6 +106,11 @@ class StatsSubmodel(C.Structure):  # grpg_stats_submodel (include/grpg_optim.h)
     _fields_ = [("n", C.c_int), ("reserved", C.c_int), ("max_radii2D", _fp), ("xyz_gradient_accum", _fp), ("denom", _fp)]
 
 
+class SkyArgs(C.Structure):  # grpg_sky_args (include/grpg_sky.h)
+    _fields_ = [("height", C.c_int), ("width", C.c_int), ("resolution", C.c_int), ("cubemap", _fp), ("ray_matrix", _fp),
+                ("jitter", _fp), ("mask", _fp), ("acc", _fp), ("fill", C.c_float), ("sky", _fp), ("stream", _fp)]
+
+
 # every symbol include/*.h declare, with its ctypes signature
 SYMBOLS = {
     "grpg_get_geometry_layout": (C.c_int, [C.c_int, C.POINTER(GeomLayout)]),
@@ -130,6 +135,9 @@ SYMBOLS = {
     "grpg_version": (C.c_int, []),
     "grpg_l1_ssim": (C.c_int, [C.POINTER(L1SsimArgs)]),
     "grpg_compose_rgb8": (C.c_int, [C.POINTER(Rgb8Args)]),
+    "grpg_sky_forward": (C.c_int, [C.POINTER(SkyArgs)]),
+    "grpg_sky_backward": (C.c_int, [C.POINTER(SkyArgs), _fp, _fp]),
+    "grpg_sky_compose_rgb8": (C.c_int, [C.POINTER(SkyArgs), _fp, _fp, _fp]),
     "grpg_adam_workspace_bytes": (C.c_size_t, [C.c_int]),
     "grpg_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int, _fp, _fp]),
     "grpg_stats_workspace_bytes": (C.c_size_t, [C.c_int]),
