@@ -32,7 +32,7 @@ void launch_packed_math_check(uint32_t first_bits, uint32_t last_bits, int negat
                               cudaStream_t stream);
 // blend_fwd.cu / blend_bwd.cu / preprocess_bwd.cu
 void launch_blend_fwd(const grpg_forward_args* a, const uint2* ranges, const uint32_t* point_list, const Rec* rec,
-                      uint32_t* n_contrib, cudaStream_t stream);
+                      uint32_t* n_contrib, long long num_instances, cudaStream_t stream);
 void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const uint32_t* point_list, const Rec* rec,
                       const uint32_t* n_contrib, float* grad_rec, cudaStream_t stream);
 void launch_preprocess_bwd(const grpg_backward_args* a, const float* cov3D, const uint8_t* clamped,
@@ -264,7 +264,7 @@ static int forward_render_impl(const grpg_forward_args* a, long long num_rendere
                          (const unsigned long long*)(g + L.num_rendered), static_capacity, device_sm_count(), stream);
     if (a->debug) if (int rc = check_cuda("binning", true, stream)) return rc;
     launch_blend_fwd(a, (const uint2*)(im + IL.ranges), b ? (const uint32_t*)(b + BL.point_list) : nullptr,
-                     (const Rec*)(g + L.rec), (uint32_t*)(im + IL.n_contrib), stream);
+                     (const Rec*)(g + L.rec), (uint32_t*)(im + IL.n_contrib), static_capacity ? 0 : num_rendered, stream);
     return check_cuda("forward_render", a->debug != 0, stream);
 }
 

@@ -103,6 +103,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 // ---- one onesweep digit pass -----------------------------------------------------------
+template <bool COMPACT>  // COMPACT: pass 0 of a compacting sort (keep_src given); false removes that code entirely
 __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift, int bits,
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     for (int i = 0; i < SORT_IPT; ++i) {
         uint32_t idx = warp_base + i * 32 + lane;
         key[i] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
-        if (keep_src != nullptr && !(idx < n && keep_src[idx] != 0u)) keep_bits &= ~(1u << i);
+        if (COMPACT && !(idx < n && keep_src[idx] != 0u)) keep_bits &= ~(1u << i);
     }
     // values are requested now so that their latency hides behind the ranking
 #pragma unroll
@@ -159,8 +160,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
         const uint32_t d = (key[i] >> shift) & mask;
-        const bool kept = (keep_bits >> i) & 1u;
-        uint32_t peers = keep_src != nullptr ? __ballot_sync(0xffffffffu, kept) : 0xffffffffu;
+        const bool kept = !COMPACT || ((keep_bits >> i) & 1u);
+        uint32_t peers = COMPACT ? __ballot_sync(0xffffffffu, kept) : 0xffffffffu;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const bool bit = (d >> b) & 1u;  // (a `b < bits` guard was measured slower than the 8 fixed ballots)
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
         if (kept && lane == leader) pre = atomicAdd(&s_warp_hist[warp][d], (uint32_t)__popc(peers));
-        pre = __shfl_sync(0xffffffffu, pre, leader < 0 ? 0 : leader);
+        pre = __shfl_sync(0xffffffffu, pre, (COMPACT && leader < 0) ? 0 : leader);
         rank[i] = (uint16_t)(pre + __popc(peers & lt_mask));
     }
     __syncthreads();
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     // scatter keys and values into tile-sorted order in shared memory
 #pragma unroll
     for (int i = 0; i < SORT_IPT; ++i) {
-        if (!((keep_bits >> i) & 1u)) continue;
+        if (COMPACT && !((keep_bits >> i) & 1u)) continue;
         uint32_t d = (key[i] >> shift) & mask;
         uint32_t p = s_local_start[d] + s_warp_hist[warp][d] + rank[i];
         s_keys[p] = key[i];
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     __syncthreads();
     // coalesced-by-run write-out: slot p of the tile goes to s_bin_base[digit] + p
     uint32_t valid = (n - tile_base) < (uint32_t)SORT_TILE ? (n - tile_base) : (uint32_t)SORT_TILE;
-    if (keep_src != nullptr) valid = tile_kept;
+    if (COMPACT) valid = tile_kept;
 #pragma unroll
     for (int k = 0; k < SORT_IPT; ++k) {
         uint32_t p = k * SORT_THREADS + tid;
@@ -360,11 +361,16 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
         //  measured for the 7-bit tile passes: 17 % fewer instructions but 104 vs 82 us per pass, bound by the
         //  dependent shared-memory chains at 3 CTAs/SM; the ballot ranking stays)
         const bool last = p == plan.passes - 1;
-        onesweep_pass_kernel<<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
-            ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
-            (iota_values && p == 0) ? 1 : 0, /*precomputed_offsets=*/1, last ? gather_src : nullptr,
-            last ? gather_dst : nullptr, (keep_src && p > 0) ? n_kept_out : n_dev, p == 0 ? keep_src : nullptr,
-            (keep_src && p == 0) ? n_kept_out : nullptr);
+        if (keep_src && p == 0)
+            onesweep_pass_kernel<true><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
+                ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
+                iota_values ? 1 : 0, /*precomputed_offsets=*/1, last ? gather_src : nullptr, last ? gather_dst : nullptr,
+                n_dev, keep_src, n_kept_out);
+        else
+            onesweep_pass_kernel<false><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
+                ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
+                (iota_values && p == 0) ? 1 : 0, /*precomputed_offsets=*/1, last ? gather_src : nullptr,
+                last ? gather_dst : nullptr, (keep_src && p > 0) ? n_kept_out : n_dev, nullptr, nullptr);
         in_a = !in_a;
     }
     return in_a;
