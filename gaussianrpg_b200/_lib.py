@@ -138,6 +138,8 @@ SYMBOLS = {
     "grpg_sky_forward": (C.c_int, [C.POINTER(SkyArgs)]),
     "grpg_sky_backward": (C.c_int, [C.POINTER(SkyArgs), _fp, _fp]),
     "grpg_sky_compose_rgb8": (C.c_int, [C.POINTER(SkyArgs), _fp, _fp, _fp]),
+    "grpg_knn_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "grpg_knn_mean_dist2": (C.c_int, [C.c_int, _fp, _fp, _fp, _fp]),
     "grpg_adam_workspace_bytes": (C.c_size_t, [C.c_int]),
     "grpg_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int, _fp, _fp]),
     "grpg_stats_workspace_bytes": (C.c_size_t, [C.c_int]),

@@ -20,7 +20,7 @@ CSRC = HERE / "csrc"
 LIB = HERE / "libgrpg_b200.so"
 OBJ_DIR = HERE / "_build"
 SOURCES = ["api.cu", "preprocess_fwd.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu",
-           "loss_ssim.cu", "image_epilogue.cu", "scene_compose.cu", "optim.cu", "sky_cubemap.cu"]
+           "loss_ssim.cu", "image_epilogue.cu", "scene_compose.cu", "optim.cu", "sky_cubemap.cu", "simple_knn.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -35,7 +35,7 @@ def _nvcc() -> str:
 
 
 def _newest_dep_mtime() -> float:
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "grpg_b200.h", HERE.parent / "include" / "grpg_loss.h", HERE.parent / "include" / "grpg_image.h", HERE.parent / "include" / "grpg_compose.h", HERE.parent / "include" / "grpg_optim.h", HERE.parent / "include" / "grpg_sky.h", Path(__file__)]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "grpg_b200.h", HERE.parent / "include" / "grpg_loss.h", HERE.parent / "include" / "grpg_image.h", HERE.parent / "include" / "grpg_compose.h", HERE.parent / "include" / "grpg_optim.h", HERE.parent / "include" / "grpg_sky.h", HERE.parent / "include" / "grpg_knn.h", Path(__file__)]
     return max(p.stat().st_mtime for p in deps)
 
 
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     nvcc = _nvcc()
     OBJ_DIR.mkdir(exist_ok=True)
-    hdr_mtime = max(p.stat().st_mtime for p in list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "grpg_b200.h", HERE.parent / "include" / "grpg_loss.h", HERE.parent / "include" / "grpg_image.h", HERE.parent / "include" / "grpg_compose.h", HERE.parent / "include" / "grpg_optim.h", HERE.parent / "include" / "grpg_sky.h"])
+    hdr_mtime = max(p.stat().st_mtime for p in list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "grpg_b200.h", HERE.parent / "include" / "grpg_loss.h", HERE.parent / "include" / "grpg_image.h", HERE.parent / "include" / "grpg_compose.h", HERE.parent / "include" / "grpg_optim.h", HERE.parent / "include" / "grpg_sky.h", HERE.parent / "include" / "grpg_knn.h"])
 
     def compile_one(src: str) -> Path:
         s = CSRC / src

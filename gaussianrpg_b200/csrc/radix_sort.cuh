@@ -41,7 +41,7 @@ static inline SortPlan make_sort_plan(int total_bits) {
 }
 
 // ---- histogram of every pass' digit in one read ---------------------------------------
-__global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+static __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n,
                                                              SortPlan plan, uint32_t* __restrict__ hist /*[passes][256]*/) {
     __shared__ uint32_t s_hist[SORT_MAX_PASSES][256];
     for (int i = threadIdx.x; i < SORT_MAX_PASSES * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
 // onesweep pass is resident at once and the decoupled look-back degenerates into a serial prefix chain
 // (measured: 30 us per pass at 2 M keys, 22 % of stall samples on the look-back load).  Reading the keys a second
 // time (4 B per pair) to precompute the offsets is cheaper.
-__global__ void __launch_bounds__(SORT_THREADS) radix_tile_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+static __global__ void __launch_bounds__(SORT_THREADS) radix_tile_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
                                                                       int shift, int bits,
                                                                       uint32_t* __restrict__ tile_hist /*[256][tiles]*/,
                                                                       const unsigned long long* __restrict__ n_dev,
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_tile_hist_kernel(const uin
 }
 
 // one CTA per digit: exclusive scan of that digit's contiguous row of tile counts (in place) + the digit total
-__global__ void __launch_bounds__(256) radix_tile_scan_kernel(uint32_t* __restrict__ tile_hist /*[256][tiles]*/,
+static __global__ void __launch_bounds__(256) radix_tile_scan_kernel(uint32_t* __restrict__ tile_hist /*[256][tiles]*/,
                                                               uint32_t tiles, uint32_t* __restrict__ digit_totals) {
     __shared__ uint32_t s_scan[8];
     uint32_t* row = tile_hist + (size_t)blockIdx.x * tiles;

@@ -52,6 +52,56 @@ def build(force: bool = False) -> Path | None:
     return DST
 
 
+KNN_SRC = Path("/root/reference/submodules/simple-knn")
+
+
+def knn_available() -> bool:
+    return any((DST / "simple_knn").glob("_C*.so"))
+
+
+def build_knn(force: bool = False) -> Path | None:
+    """The UNMODIFIED simple-knn extension (distCUDA2), same recipe; `-include cfloat` supplies FLT_MAX, which
+    simple_knn.cu uses without including <cfloat> (a flag, not a source edit)."""
+    if knn_available() and not force:
+        return DST
+    if not KNN_SRC.exists():
+        return None
+    with tempfile.TemporaryDirectory(prefix="grpg_refbuild_") as tmp:
+        work = Path(tmp) / "knn"
+        shutil.copytree(KNN_SRC, work, ignore=shutil.ignore_patterns("dist", "*.egg-info", "build"))
+        env = dict(os.environ, TORCH_CUDA_ARCH_LIST="10.0a", NVCC_APPEND_FLAGS="-include cfloat", MAX_JOBS="6")
+        r = subprocess.run([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=work, env=env,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("reference simple-knn build failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+        pkg = DST / "simple_knn"
+        if pkg.exists():
+            shutil.rmtree(pkg)
+        pkg.mkdir(parents=True)
+        (pkg / "__init__.py").write_text("")
+        for f in (work / "simple_knn").iterdir():
+            if f.suffix == ".so":
+                shutil.copy2(f, pkg / f.name)
+    return DST
+
+
+def load_knn():
+    """The reference's `simple_knn._C` under a private name (ours owns `simple_knn`)."""
+    import importlib.util
+    if not knn_available():
+        raise RuntimeError("oracle/_ref/simple_knn is not built")
+    name = "_grpg_reference_simple_knn_C"
+    if name in sys.modules:
+        return sys.modules[name]
+    import torch  # noqa: F401
+    so = next((DST / "simple_knn").glob("_C*.so"))
+    spec = importlib.util.spec_from_file_location("_C", so)  # the module's PyInit symbol is PyInit__C
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules[name] = mod
+    return mod
+
+
 def load():
     """Import the reference package under a private name (ours owns `diff_gaussian_rasterization`)."""
     import importlib.util
@@ -71,3 +121,4 @@ def load():
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build_knn(force="--force" in sys.argv))

@@ -28,6 +28,7 @@
  * (tests/golden/*.npz, generated on a B200 by tests/golden/make_golden.py).
  */
 #include <math.h>
+#include <float.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -597,6 +598,25 @@ void oracle_preprocess_backward(int P, int D, int M, const float* means3D, const
             dL_drot[4 * i + 3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) +
                                  2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
         }
+    }
+}
+
+/* ---- simple-knn distCUDA2 (reference submodules/simple-knn/simple_knn.cu:127-183): for every point the mean of the
+ * three smallest squared distances to the OTHER points, each distance rounded like the reference build rounds
+ * `d.x*d.x + d.y*d.y + d.z*d.z` (d = other - point; SASS: FMUL, FFMA, FFMA), summed smallest first, divided by 3.
+ * Brute force O(P^2): the reference's Morton/box search is exact, so its result does not depend on the search. */
+void oracle_knn_mean_dist2(int P, const float* pts, float* out) {
+    for (int i = 0; i < P; ++i) {
+        float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+        const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        for (int j = 0; j < P; ++j) {
+            if (j == i) continue;
+            const float dx = pts[3 * j] - x, dy = pts[3 * j + 1] - y, dz = pts[3 * j + 2] - z;
+            float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            for (int k = 0; k < 3; ++k)
+                if (best[k] > d) { const float t = best[k]; best[k] = d; d = t; }
+        }
+        out[i] = ((best[0] + best[1]) + best[2]) / 3.0f;
     }
 }
 

@@ -145,3 +145,12 @@ def backward(means3D, view, proj, campos, W, H, tan_fovx, tan_fovy, bg, pre, bin
         _p(out["dL_dcolors"]), _p(g["depths"]), _p(out["dL_dmeans3D"]), _p(out["dL_dcov3D"]), _p(out["dL_dsh"]),
         _p(out["dL_dscales"]), _p(out["dL_drotations"]))
     return out
+
+
+def knn_mean_dist2(points):
+    """simple-knn distCUDA2 by brute force (oracle_knn_mean_dist2): float32 [P]."""
+    lib = load()
+    pts = _f(points).reshape(-1, 3)
+    out = np.empty(pts.shape[0], dtype=np.float32)
+    lib.oracle_knn_mean_dist2(C.c_int(pts.shape[0]), _p(pts), _p(out))
+    return out

@@ -96,7 +96,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
                "grpg_compose_submodel": _lib.ComposeSubmodel,
                "grpg_adam_tensor": _lib.AdamTensor, "grpg_stats_submodel": _lib.StatsSubmodel,
                "grpg_sky_args": _lib.SkyArgs}
-    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grpg_b200.h"', '#include "grpg_loss.h"', '#include "grpg_image.h"', '#include "grpg_compose.h"', '#include "grpg_optim.h"', '#include "grpg_sky.h"',
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grpg_b200.h"', '#include "grpg_loss.h"', '#include "grpg_image.h"', '#include "grpg_compose.h"', '#include "grpg_optim.h"', '#include "grpg_sky.h"', '#include "grpg_knn.h"',
              'int main(void){']
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} sizeof %zu\\n", sizeof({cname}));')
