@@ -257,7 +257,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist_on = world > 1
+    # GRPG_BENCH_FORCE_SHARDED=1 (under torchrun --nproc-per-node 1): run the sharded path on one GPU (debugging aid)
+    dist_on = world > 1 or bool(os.environ.get("GRPG_BENCH_FORCE_SHARDED"))
     if args.impl == "reference" and rank != 0:
         return  # reference arm: rank 0 alone runs and prints
     if not torch.cuda.is_available():
@@ -281,11 +282,15 @@ def main():
         if rank == 0:
             clk = clocks.stop()
             result["clocks"] = {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]}
-            print(json.dumps(result))
+            print(json.dumps(result), flush=True)
         import torch.distributed as dist
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
-        return
+        # Tearing down a NCCL communicator that CUDA graphs have captured work on can block in the interpreter's
+        # finalisers (seen on 2 GPUs); the measurement is complete and printed, so leave without running them.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
     H, W = sc_cpu.height, sc_cpu.width
     workload = f"street scene {sc_cpu.means3D.shape[0]} Gaussians (1.84M bkgd + 8x20k actors), SH deg 1, {W}x{H}, fwd+bwd"
@@ -416,7 +421,7 @@ def main():
             gstate = {}
 
             def gstep():
-                gstate["loss"] = fwd_bwd(cam_s[:16].view(4, 4), cam_s[16:32].view(4, 4), cam_s[32:35], gt_s)
+                gstate["loss"] = fwd_bwd(cam_s[:16].view(4, 4), cam_s[16:32].view(4, 4), cam_s[32:35], gt_s).detach()
 
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -426,8 +431,9 @@ def main():
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             _gC.check_static_binning()
+            gstate.clear()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 gstep()
             for _ in range(3):
                 graph.replay()

@@ -322,7 +322,6 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
     gt_b, wd_b, wa_b = (frame_to_band(t, world, rank) for t in (gt, w_depth, w_alpha))
     n_pix = float(H * W)
     leaves = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
-    means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
     rast_train = ShardedGaussianRasterizer(sc.settings(), output="band", gradients="shard")
     rast_frame = ShardedGaussianRasterizer(sc.settings(), output="frame", gradients="full")
     kw = lambda: dict(means3D=leaves["means3D"], opacities=leaves["opacities"], shs=leaves["shs"],  # noqa: E731
@@ -339,12 +338,14 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
     def train_step(gt_band=gt_b):
         for v in leaves.values():
             v.grad = None
-        means2D.grad = None
+        means2D = torch.zeros(P, 3, device=dev, requires_grad=True)  # street_gaussian_renderer.py:158
         color, radii, depth, alpha, _ = rast_train(means2D=means2D, **kw())
         loss = band_loss(color, depth, alpha, gt_band)
         loss.backward()
-        state["loss"] = loss
-        return loss
+        # only detached results outlive the step: a retained autograd graph would keep the leaves' AccumulateGrad nodes
+        # bound to the stream of an earlier iteration, which breaks stream capture
+        state["loss"], state["means2D_grad"] = loss.detach(), means2D.grad
+        return state["loss"]
 
     def fwd_only():
         with torch.no_grad():
@@ -377,7 +378,7 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
     frame_want = torch.cat([color, depth, alpha], 0).detach()
     train_step()
     got = {k: v.grad.clone() for k, v in leaves.items()}
-    got["means2D"] = means2D.grad.clone()
+    got["means2D"] = state["means2D_grad"].clone()
     p_begin, p_count = gaussian_slice(P, world, rank)
     parity = {"grad_shard_max_rel": {}, "grad_outside_shard_nonzero": 0}
     for k_ in got:
@@ -444,8 +445,10 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             dist.barrier()
+            state.clear()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: NCCL's watchdog thread may query its events while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 train_step()
             graph.replay()
             torch.cuda.synchronize()
@@ -454,7 +457,10 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
         except Exception as exc:  # capture of the collective is the fragile part: fall back to eager launches
             graph = None
             graph_note = f"eager (graph capture failed: {exc!r})"[:300]
-            torch.cuda.synchronize()
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
     step_fn = graph.replay if graph is not None else train_step
     for _ in range(max(3, args.warmup)):
         step_fn()
@@ -545,6 +551,11 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
     launches = sum(v["launches_per_step"] for v in kern.values())
     xs = sorted(per_step)
     q = lambda f: xs[min(len(xs) - 1, max(0, int(round(f * (len(xs) - 1)))))]  # noqa: E731
+    if graph is not None:  # a live graph holds NCCL resources: release it before the process group goes away
+        del graph, step_fn
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
     band_bytes = 5 * max_band_rows(H, world) * TILE * W * 4
     return {
         "metric": "iters_per_sec_fwd_bwd_1920x1280_2M", "value": 1000.0 * args.steps / ms_fb, "unit": "iters/s",

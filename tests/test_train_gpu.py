@@ -44,11 +44,11 @@ def test_training_trajectory_matches_the_reference_arm(cuda_device):
     assert o["P_end"] != o["P_start"]
     # Gaussian counts after each densify: equal up to threshold flips of borderline Gaussians (the accumulated
     # statistics differ by ~1e-5 relative between the arms).  The first event sees the same model in both arms: 0.1 %;
-    # afterwards the arms hold slightly different point sets and the flips compound: 1 %.  The counts are printed.
+    # afterwards the arms hold slightly different point sets and the flips compound: 3 %.  The counts are printed.
     for n_ev, it in enumerate(densify_at):
         so, sr = o["sizes"][it][0], r["sizes"][it][0]
         for a, b in zip(so, sr):
-            assert abs(a - b) <= max(3, int((0.001 if n_ev == 0 else 0.01) * b)), (it, so, sr)
+            assert abs(a - b) <= max(3, int((0.001 if n_ev == 0 else 0.03) * b)), (it, so, sr)
     print("P after densify (ours / reference):", {it: (sum(o["sizes"][it][0]), sum(r["sizes"][it][0])) for it in densify_at})
     # Loss trajectories.  Up to the first densify both arms hold the same model: the curves agree iteration by
     # iteration.  One borderline Gaussian flipping across a threshold (65944 vs 65945 points after the first event in the

@@ -86,7 +86,7 @@ def step():
     out = rast(means3D=leaves["means3D"], means2D=None, opacities=leaves["opacities"], shs=leaves["shs"],
                scales=leaves["scales"], rotations=leaves["rotations"])
     ((out[0] * w[0]).sum() + (out[2] * w[1]).sum() + (out[3] * w[2]).sum()).backward()
-    hold["color"] = out[0]
+    hold["color"] = out[0].detach()
 
 
 try:
@@ -97,8 +97,9 @@ try:
             step()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize(); dist.barrier()
+    hold.clear()
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
         step()
     for _ in range(3):
         graph.replay()
@@ -126,6 +127,8 @@ except Exception as exc:
     if rank == 0:
         print("CUDA graph capture of the training step failed:", repr(exc)[:500], flush=True)
 grpg.set_static_binning(None)
+torch.cuda.synchronize()
 dist.barrier()
-dist.destroy_process_group()
-sys.exit(1 if fail else 0)
+# a NCCL communicator with captured graphs can block in the finalisers: the check is complete, leave without them
+sys.stdout.flush(); sys.stderr.flush()
+os._exit(1 if fail else 0)
