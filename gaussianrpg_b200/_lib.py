@@ -111,6 +111,11 @@ class SkyArgs(C.Structure):  # grpg_sky_args (include/grpg_sky.h)
                 ("jitter", _fp), ("mask", _fp), ("acc", _fp), ("fill", C.c_float), ("sky", _fp), ("stream", _fp)]
 
 
+class ExchangeArgs(C.Structure):  # grpg_exchange_args (include/grpg_b200.h)
+    _fields_ = [("P", C.c_int), ("world", C.c_int), ("rank", C.c_int), ("geom_ws", _fp), ("grad_rec", _fp),
+                ("inbox", _fp * 8), ("stream", _fp)]
+
+
 # every symbol include/*.h declare, with its ctypes signature
 SYMBOLS = {
     "grpg_get_geometry_layout": (C.c_int, [C.c_int, C.POINTER(GeomLayout)]),
@@ -122,6 +127,9 @@ SYMBOLS = {
     "grpg_forward_render": (C.c_int, [C.POINTER(ForwardArgs), C.c_int]),
     "grpg_forward": (C.c_int, [C.POINTER(ForwardArgs), C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "grpg_forward_static": (C.c_int, [C.POINTER(ForwardArgs), C.c_longlong, _fp]),
+    "grpg_exchange_inbox_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "grpg_exchange_pack": (C.c_int, [C.POINTER(ExchangeArgs)]),
+    "grpg_exchange_accumulate": (C.c_int, [C.POINTER(ExchangeArgs)]),
     "grpg_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "grpg_backward": (C.c_int, [C.POINTER(BackwardArgs)]),
     "grpg_mark_visible": (C.c_int, [C.c_int, _fp, _fp, _fp, _fp, _fp]),

@@ -20,7 +20,7 @@ CSRC = HERE / "csrc"
 LIB = HERE / "libgrpg_b200.so"
 OBJ_DIR = HERE / "_build"
 SOURCES = ["api.cu", "preprocess_fwd.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu",
-           "loss_ssim.cu", "image_epilogue.cu", "scene_compose.cu", "optim.cu", "sky_cubemap.cu", "simple_knn.cu"]
+           "loss_ssim.cu", "image_epilogue.cu", "scene_compose.cu", "optim.cu", "sky_cubemap.cu", "simple_knn.cu", "record_exchange.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -1,0 +1,125 @@
+// record_exchange.cu -- sparse exchange of the per-Gaussian 2D gradient records between the ranks of a tile-row sharded
+// frame over NVLink peer memory (include/grpg_b200.h, grpg_exchange_*).  No reference counterpart.
+#include <cstdint>
+#include "grpg_common.cuh"
+
+extern "C" int grpg_loss_fail(const char* msg);
+
+namespace grpg {
+
+constexpr int EX_HEADER = 256;      // bytes: [0..7] u32 counts received per source rank, [8..15] u32 send counters (local use)
+constexpr int EX_ENTRY = 12;        // floats per entry: Gaussian id (bits) + the 11 record components = 48 bytes
+
+static inline size_t ex_slice(int P, int world) { return ((size_t)P + world - 1) / world; }
+
+struct ExPtrs { char* inbox[8]; };
+
+// One thread per Gaussian.  In-band Gaussians (tiles_touched != 0) of a foreign slice are appended to the owner's inbox
+// segment reserved for this rank; slots are allocated per warp (owners are monotone in the id, so a warp addresses one
+// or two owners) with one atomic on a LOCAL counter, the 48-byte entry itself is a peer store.
+__global__ void __launch_bounds__(256) exchange_pack_kernel(int P, int world, int rank, uint32_t slice,
+                                                            const uint32_t* __restrict__ tiles_touched,
+                                                            const float4* __restrict__ grad_rec4, ExPtrs ptrs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t* send_count = reinterpret_cast<uint32_t*>(ptrs.inbox[rank]) + 8;
+    const bool in_range = i < (uint32_t)P;
+    const int owner = in_range ? (int)(i / slice) : -1;
+    bool send = in_range && owner != rank && tiles_touched[i] != 0u;
+    uint32_t todo = __ballot_sync(0xffffffffu, send);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int lead_owner = __shfl_sync(0xffffffffu, owner, leader);
+        const uint32_t peers = __ballot_sync(0xffffffffu, send && owner == lead_owner);
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(send_count + lead_owner, (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (send && owner == lead_owner) {
+            const uint32_t slot = base + __popc(peers & ((1u << lane) - 1u));
+            float4* dst = reinterpret_cast<float4*>(ptrs.inbox[owner] + EX_HEADER + ((size_t)rank * slice + slot) * (EX_ENTRY * 4));
+            const float4 a = grad_rec4[3 * (size_t)i], b = grad_rec4[3 * (size_t)i + 1], c = grad_rec4[3 * (size_t)i + 2];
+            dst[0] = make_float4(__uint_as_float(i), a.x, a.y, a.z);
+            dst[1] = make_float4(a.w, b.x, b.y, b.z);
+            dst[2] = make_float4(b.w, c.x, c.y, c.z);
+            send = false;
+        }
+        todo &= ~peers;
+    }
+}
+
+// publishes how many entries this rank appended to every owner's inbox (remote 4-byte stores into the headers)
+__global__ void exchange_publish_kernel(int world, int rank, ExPtrs ptrs) {
+    const int q = threadIdx.x;
+    if (q >= world || q == rank) return;
+    const uint32_t* send_count = reinterpret_cast<const uint32_t*>(ptrs.inbox[rank]) + 8;
+    reinterpret_cast<uint32_t*>(ptrs.inbox[q])[rank] = send_count[q];
+}
+
+// one warp per inbox entry: lanes 0..10 add the record's components (one coalesced RED per entry)
+__global__ void __launch_bounds__(256) exchange_accumulate_kernel(int world, int rank, uint32_t slice, const char* __restrict__ inbox,
+                                                                  float* __restrict__ grad_rec) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t* counts = reinterpret_cast<const uint32_t*>(inbox);
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        const uint32_t n = min(counts[q], slice);
+        const float* seg = reinterpret_cast<const float*>(inbox + EX_HEADER + (size_t)q * slice * (EX_ENTRY * 4));
+        for (uint32_t e = warp; e < n; e += n_warps) {
+            const float v = lane < 12 ? seg[(size_t)e * EX_ENTRY + lane] : 0.f;
+            const uint32_t id = __float_as_uint(__shfl_sync(0xffffffffu, v, 0));
+            if (lane >= 1 && lane < 12) atomicAdd(grad_rec + (size_t)id * 12 + (lane - 1), v);
+        }
+    }
+}
+
+}  // namespace grpg
+
+using namespace grpg;
+
+extern "C" size_t grpg_exchange_inbox_bytes(int P, int world) {
+    if (P < 0 || world < 1 || world > 8) return 0;
+    return EX_HEADER + ex_slice(P, world) * (size_t)world * (EX_ENTRY * 4);
+}
+
+static int ex_check(const grpg_exchange_args* a, ExPtrs& p) {
+    if (!a || a->P < 0 || a->world < 1 || a->world > 8 || a->rank < 0 || a->rank >= a->world)
+        return grpg_loss_fail("grpg_exchange: bad arguments");
+    if (!a->grad_rec || !a->geom_ws) return grpg_loss_fail("grpg_exchange: missing buffers");
+    for (int q = 0; q < a->world; ++q) {
+        if (!a->inbox[q]) return grpg_loss_fail("grpg_exchange: missing inbox pointer");
+        p.inbox[q] = (char*)a->inbox[q];
+    }
+    return 0;
+}
+
+extern "C" int grpg_exchange_pack(const grpg_exchange_args* a) {
+    ExPtrs p{};
+    if (int rc = ex_check(a, p)) return rc;
+    if (a->P == 0 || a->world == 1) return 0;
+    cudaStream_t stream = (cudaStream_t)a->stream;
+    grpg_geom_layout L;
+    grpg_get_geometry_layout(a->P, &L);
+    const uint32_t* tiles_touched = (const uint32_t*)((const char*)a->geom_ws + L.tiles_touched);
+    ProfScope ps("exchange_pack", stream);
+    cudaMemsetAsync(p.inbox[a->rank] + 32, 0, 32, stream);  // this rank's send counters
+    exchange_pack_kernel<<<(a->P + 255) / 256, 256, 0, stream>>>(a->P, a->world, a->rank, (uint32_t)ex_slice(a->P, a->world),
+                                                                 tiles_touched, reinterpret_cast<const float4*>(a->grad_rec), p);
+    exchange_publish_kernel<<<1, 32, 0, stream>>>(a->world, a->rank, p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return grpg_loss_fail(cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int grpg_exchange_accumulate(const grpg_exchange_args* a) {
+    ExPtrs p{};
+    if (int rc = ex_check(a, p)) return rc;
+    if (a->P == 0 || a->world == 1) return 0;
+    cudaStream_t stream = (cudaStream_t)a->stream;
+    ProfScope ps("exchange_accumulate", stream);
+    exchange_accumulate_kernel<<<148 * 4, 256, 0, stream>>>(a->world, a->rank, (uint32_t)ex_slice(a->P, a->world),
+                                                            p.inbox[a->rank], a->grad_rec);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return grpg_loss_fail(cudaGetErrorString(e));
+    return 0;
+}

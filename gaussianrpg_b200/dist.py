@@ -48,6 +48,8 @@ def max_band_rows(H: int, k: int) -> int:
 def frame_to_band(full: torch.Tensor, k: int, r: int) -> torch.Tensor:
     """[C,H,W] frame -> compact band image [C, band_rows*16, W] of rank r (zero padded below the frame)."""
     C, H, W = full.shape
+    if k <= 1:
+        return full.contiguous()  # one rank: the band is the frame (no tile padding, like the library's band_height)
     lr_max = max_band_rows(H, k)
     pad = lr_max * k * TILE - H
     x = torch.nn.functional.pad(full, (0, 0, 0, pad)) if pad else full
@@ -146,6 +148,67 @@ class _PeerFrame:
 
 
 FUSED_FORWARD_GATHER = True  # set False to force the NCCL all-gather path
+# gradients="shard": exchange only the records of the Gaussians that touch the rank's rows, by peer stores into the
+# owner's inbox (grpg_exchange_pack / _accumulate), instead of reduce-scattering the dense [P,12] buffer with NCCL
+import os as _os
+SPARSE_RECORD_EXCHANGE = _os.environ.get("GRPG_SPARSE_EXCHANGE", "1") != "0"
+
+
+class _PeerInbox:
+    """Peer-mapped inboxes of the sparse record exchange (torch symmetric memory), two alternating buffers (see
+    _PeerFrame for why one barrier per step is enough then)."""
+    _cache = {}
+
+    def __init__(self, P: int, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        k = dist.get_world_size(group)
+        nbytes = int(_lib.load().grpg_exchange_inbox_bytes(P, k))
+        self.bufs, self.handles, self.ptrs = [], [], []
+        for _ in range(2):
+            b = symm_mem.empty((nbytes,), dtype=torch.uint8, device=device)
+            h = symm_mem.rendezvous(b, group)
+            b.zero_()
+            self.bufs.append(b); self.handles.append(h); self.ptrs.append([int(p) for p in h.buffer_ptrs])
+        self.turn = 0
+
+    @classmethod
+    def get(cls, P, device, group):
+        key = (P, str(device), id(group))
+        if key not in cls._cache:
+            try:
+                cls._cache[key] = cls(P, device, group)
+            except Exception as exc:
+                cls._cache[key] = None
+                if dist.get_rank(group) == 0:
+                    print(f"[gaussianrpg_b200.dist] symmetric memory unavailable ({exc!r}); using NCCL reduce-scatter")
+        return cls._cache[key]
+
+
+def _exchange_args(P, k, r, geom, grad_rec, ptrs, dev):
+    from . import _lib
+    a = _lib.ExchangeArgs()
+    a.P, a.world, a.rank = int(P), int(k), int(r)
+    a.geom_ws, a.grad_rec = geom.data_ptr(), grad_rec.data_ptr()
+    for q in range(k):
+        a.inbox[q] = int(ptrs[q])
+    a.stream = _lib.current_stream_ptr(dev)
+    return a
+
+
+def sparse_record_exchange(P, k, r, geom, grad_rec, inbox_ptrs, barrier, dev):
+    """pack -> barrier between the ranks -> accumulate (see include/grpg_b200.h, grpg_exchange_*).  `barrier` is a
+    callable; `inbox_ptrs[q]` the (peer-mapped) inbox of rank q.  Afterwards grad_rec's own slice is complete."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    a = _exchange_args(P, k, r, geom, grad_rec, inbox_ptrs, dev)
+    with torch.cuda.device(dev):
+        if lib.grpg_exchange_pack(C.byref(a)) != 0:
+            raise RuntimeError(_lib.last_error())
+        barrier()
+        if lib.grpg_exchange_accumulate(C.byref(a)) != 0:
+            raise RuntimeError(_lib.last_error())
 
 
 def _forward_band(rs, tensors, k, r, peer_ptrs=None, forward_only=False):
@@ -236,8 +299,19 @@ class _ShardedRasterize(torch.autograd.Function):
                 *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _width=W, _stage=2,
                 _grad_rec=grad_rec, _slice=(0, P), _wanted=wanted)
         else:
-            mine = _reduce_scatter_rows(grad_rec, group, k, r)  # grad_rec has padded_count(P, k) rows
             p_begin, p_count = gaussian_slice(P, k, r)
+            inbox = None
+            if (SPARSE_RECORD_EXCHANGE and 1 < k <= 8 and means3D.is_cuda and dist.get_backend(group) == "nccl"
+                    and _native is None):
+                inbox = _PeerInbox.get(P, means3D.device, group)
+            if inbox is not None:
+                turn = inbox.turn
+                inbox.turn ^= 1
+                sparse_record_exchange(P, k, r, geom, grad_rec, inbox.ptrs[turn],
+                                       lambda: inbox.handles[turn].barrier(channel=0), means3D.device)
+                mine = grad_rec[p_begin:p_begin + max(p_count, 1)]
+            else:
+                mine = _reduce_scatter_rows(grad_rec, group, k, r)  # grad_rec has padded_count(P, k) rows
             shard = C_.rasterize_gaussians_backward(
                 *common, g_color, g_depth, g_alpha, g_sem, *tail, _band=(k, r), _height=H, _width=W, _stage=2,
                 _grad_rec=mine, _slice=(p_begin, p_count), _wanted=wanted, _full_rows=True)
@@ -571,9 +645,13 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
         "execution": graph_note,
         "kernels": kern, "kernels_note": f"rank {rank}, CUDA events around every library launch of one eager step",
         "library_ms_per_step_rank0": lib_ms,
-        "collectives": {"reduce_scatter_records_ms": rs_ms, "bytes_per_rank_in": 48 * padded_count(P, world),
-                        "note": "NCCL reduce-scatter of the [P,12] float record buffer timed alone (5 calls, CUDA events); inside "
-                                "the step it is one node of the graph"},
+        "collectives": {"record_exchange": ("sparse peer-store exchange (grpg_exchange_pack / _accumulate over NVLink symmetric "
+                                            "memory, one barrier): see kernels.exchange_pack / exchange_accumulate"
+                                            if (SPARSE_RECORD_EXCHANGE and any(v is not None for v in _PeerInbox._cache.values()))
+                                            else "NCCL reduce-scatter of the dense record buffer"),
+                        "reduce_scatter_records_ms": rs_ms, "bytes_per_rank_in": 48 * padded_count(P, world),
+                        "note": "reduce_scatter_records_ms = NCCL reduce-scatter of the dense [P,12] float record buffer timed "
+                                "alone (5 calls, CUDA events), for comparison with the exchange kernels"},
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": alg[dom],

@@ -257,6 +257,35 @@ int grpg_visible_filter(int P, int width, int height,
                         float tan_fovx, float tan_fovy,
                         int* radii, float* means2D, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Multi-GPU gradient-record exchange over NVLink peer memory (no reference    */
+/* counterpart).  After the blend backward of a tile-row band, rank  */
+/* r holds partial 48-byte records for the Gaussians that touch ITS rows only   */
+/* (a quarter of them on 8 GPUs); the per-Gaussian backward of Gaussian g runs   */
+/* on the rank that owns g's slice of the Gaussian axis (slice = ceil(P/world)   */
+/* consecutive ids).  Instead of reduce-scattering the dense [P,12] buffer      */
+/* (96 MB per rank at 2 M Gaussians), grpg_exchange_pack stores the (id, record) */
+/* pairs of the in-band Gaussians straight into the owner's inbox through        */
+/* peer-mapped pointers (48-byte entries, warp-aggregated slot allocation), and  */
+/* after a barrier between the ranks grpg_exchange_accumulate adds the entries   */
+/* of the local inbox into the local record buffer.  Worst-case capacity (every  */
+/* Gaussian of a slice from every peer) is reserved, so there is no overflow.    */
+/* ------------------------------------------------------------------------- */
+typedef struct grpg_exchange_args {
+    int P, world, rank;
+    const void* geom_ws;     /* this rank's forward geometry workspace (which Gaussians are in the band)          */
+    float* grad_rec;         /* [>= P, 12] device: partial records in, (own slice) complete records out            */
+    void* inbox[8];          /* inbox[q]: peer-mapped base of rank q's inbox (inbox[rank] is local memory)         */
+    void* stream;
+} grpg_exchange_args;
+
+size_t grpg_exchange_inbox_bytes(int P, int world);
+/* stores this rank's in-band records of foreign slices into their owners' inboxes and publishes the counts */
+int grpg_exchange_pack(const grpg_exchange_args* a);
+/* to be called after every rank's grpg_exchange_pack has completed (caller's barrier): adds the local inbox's entries
+ * into grad_rec; afterwards rows [rank*slice, (rank+1)*slice) of grad_rec hold the sums over all ranks */
+int grpg_exchange_accumulate(const grpg_exchange_args* a);
+
 /* Reconstructs the reference's sorted 64-bit keys ((tile << 32) | depth bits,
  * rasterizer_impl.cu:102-104) from our workspaces -- test hook for the bit-exact
  * key comparison. */

@@ -95,7 +95,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
                "grpg_image_layout": _lib.ImageLayout, "grpg_l1_ssim_args": _lib.L1SsimArgs, "grpg_rgb8_args": _lib.Rgb8Args,
                "grpg_compose_submodel": _lib.ComposeSubmodel,
                "grpg_adam_tensor": _lib.AdamTensor, "grpg_stats_submodel": _lib.StatsSubmodel,
-               "grpg_sky_args": _lib.SkyArgs}
+               "grpg_sky_args": _lib.SkyArgs, "grpg_exchange_args": _lib.ExchangeArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "grpg_b200.h"', '#include "grpg_loss.h"', '#include "grpg_image.h"', '#include "grpg_compose.h"', '#include "grpg_optim.h"', '#include "grpg_sky.h"', '#include "grpg_knn.h"',
              'int main(void){']
     for cname, ct in structs.items():
