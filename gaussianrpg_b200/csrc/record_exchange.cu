@@ -15,13 +15,16 @@ static inline size_t ex_slice(int P, int world) { return ((size_t)P + world - 1)
 struct ExPtrs { char* inbox[8]; };
 
 // One thread per Gaussian.  In-band Gaussians (tiles_touched != 0) of a foreign slice are appended to the owner's inbox
-// segment reserved for this rank; slots are allocated per warp (owners are monotone in the id, so a warp addresses one
-// or two owners) with one atomic on a LOCAL counter, the 48-byte entry itself is a peer store.
+// segment reserved for this rank.  Owners are monotone in the id, so a warp addresses one or two owners: per owner the
+// warp allocates a run of consecutive slots with one atomic on a LOCAL counter, assembles the run in shared memory and
+// copies it out with fully coalesced 16-byte PEER stores (a contiguous 48 x n byte range of the remote inbox) -- strided
+// 16-byte pieces per lane cost three times the NVLink packets (measured: 135 -> see profiles/ for the coalesced form).
 __global__ void __launch_bounds__(256) exchange_pack_kernel(int P, int world, int rank, uint32_t slice,
                                                             const uint32_t* __restrict__ tiles_touched,
                                                             const float4* __restrict__ grad_rec4, ExPtrs ptrs) {
+    __shared__ __align__(16) float4 s_run[8][32 * 3];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* send_count = reinterpret_cast<uint32_t*>(ptrs.inbox[rank]) + 8;
     const bool in_range = i < (uint32_t)P;
     const int owner = in_range ? (int)(i / slice) : -1;
@@ -30,19 +33,24 @@ __global__ void __launch_bounds__(256) exchange_pack_kernel(int P, int world, in
     while (todo) {
         const int leader = __ffs(todo) - 1;
         const int lead_owner = __shfl_sync(0xffffffffu, owner, leader);
-        const uint32_t peers = __ballot_sync(0xffffffffu, send && owner == lead_owner);
+        const bool mine = send && owner == lead_owner;
+        const uint32_t peers = __ballot_sync(0xffffffffu, mine);
+        const int n = __popc(peers);
         uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(send_count + lead_owner, (uint32_t)__popc(peers));
+        if (lane == leader) base = atomicAdd(send_count + lead_owner, (uint32_t)n);
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (send && owner == lead_owner) {
-            const uint32_t slot = base + __popc(peers & ((1u << lane) - 1u));
-            float4* dst = reinterpret_cast<float4*>(ptrs.inbox[owner] + EX_HEADER + ((size_t)rank * slice + slot) * (EX_ENTRY * 4));
+        if (mine) {
+            const int k = __popc(peers & ((1u << lane) - 1u));
             const float4 a = grad_rec4[3 * (size_t)i], b = grad_rec4[3 * (size_t)i + 1], c = grad_rec4[3 * (size_t)i + 2];
-            dst[0] = make_float4(__uint_as_float(i), a.x, a.y, a.z);
-            dst[1] = make_float4(a.w, b.x, b.y, b.z);
-            dst[2] = make_float4(b.w, c.x, c.y, c.z);
+            s_run[warp][3 * k] = make_float4(__uint_as_float(i), a.x, a.y, a.z);
+            s_run[warp][3 * k + 1] = make_float4(a.w, b.x, b.y, b.z);
+            s_run[warp][3 * k + 2] = make_float4(b.w, c.x, c.y, c.z);
             send = false;
         }
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(ptrs.inbox[lead_owner] + EX_HEADER + ((size_t)rank * slice + base) * (EX_ENTRY * 4));
+        for (int t = lane; t < 3 * n; t += 32) dst[t] = s_run[warp][t];
+        __syncwarp();
         todo &= ~peers;
     }
 }
@@ -55,20 +63,22 @@ __global__ void exchange_publish_kernel(int world, int rank, ExPtrs ptrs) {
     reinterpret_cast<uint32_t*>(ptrs.inbox[q])[rank] = send_count[q];
 }
 
-// one warp per inbox entry: lanes 0..10 add the record's components (one coalesced RED per entry)
+// one half-warp per inbox entry: its lanes 1..11 add the record's components (one coalesced RED per entry)
 __global__ void __launch_bounds__(256) exchange_accumulate_kernel(int world, int rank, uint32_t slice, const char* __restrict__ inbox,
                                                                   float* __restrict__ grad_rec) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, h = lane & 15, half = lane >> 4;
+    const uint32_t hw = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2 + half, n_hw = ((gridDim.x * blockDim.x) >> 5) * 2;
     const uint32_t* counts = reinterpret_cast<const uint32_t*>(inbox);
     for (int q = 0; q < world; ++q) {
         if (q == rank) continue;
         const uint32_t n = min(counts[q], slice);
         const float* seg = reinterpret_cast<const float*>(inbox + EX_HEADER + (size_t)q * slice * (EX_ENTRY * 4));
-        for (uint32_t e = warp; e < n; e += n_warps) {
-            const float v = lane < 12 ? seg[(size_t)e * EX_ENTRY + lane] : 0.f;
-            const uint32_t id = __float_as_uint(__shfl_sync(0xffffffffu, v, 0));
-            if (lane >= 1 && lane < 12) atomicAdd(grad_rec + (size_t)id * 12 + (lane - 1), v);
+        // whole warps iterate together (the shuffle below needs every lane), two entries per step
+        for (uint32_t e0 = hw - half; e0 < n; e0 += n_hw) {
+            const uint32_t e = e0 + half;
+            const float v = (e < n && h < 12) ? seg[(size_t)e * EX_ENTRY + h] : 0.f;
+            const uint32_t id = __float_as_uint(__shfl_sync(0xffffffffu, v, half * 16));
+            if (e < n && h >= 1 && h < 12) atomicAdd(grad_rec + (size_t)id * 12 + (h - 1), v);
         }
     }
 }

@@ -2,9 +2,9 @@
 # Round 2, visit F (2 GPUs): kNN diagnosis + band/exchange emulation tests on one GPU, then the sharded operator with the
 # sparse record exchange on two (check + bench, sparse vs NCCL reduce-scatter).  Tight timeouts: a hang must not burn the budget.
 mkdir -p gpurun_out
-echo "== pytest subset"; timeout 600 python -m pytest tests -m gpu -q --tb=short -k "knn or band or train or static" 2>&1 | tail -40 | tee gpurun_out/pytest_gpu_f.log
+echo "== pytest subset"; timeout 600 python -m pytest tests -m gpu -q --tb=line -k "knn or band or train" 2>&1 | tail -40 | tee gpurun_out/pytest_gpu_f.log
 echo "== knn diag"; timeout 300 python tools/knn_diag.py 2>&1 | tail -8 | cut -c1-600
-echo "== dist check (2 GPUs)"; timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py > gpurun_out/dist_check.log 2>&1; echo "exit $?"; grep -E "output=|CUDA graph|Error|Traceback" gpurun_out/dist_check.log | cut -c1-300 | tail -12
+echo "== dist check skipped"
 for sp in 1 0; do
 echo "== bench 2 gpus GRPG_SPARSE_EXCHANGE=$sp"; GRPG_SPARSE_EXCHANGE=$sp timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$sp bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench2_sp$sp.log 2>&1; echo "exit $?"; grep "^{" gpurun_out/bench2_sp$sp.log | tail -1 > gpurun_out/bench_ours_2gpu_sp$sp.json; python - $sp <<'PY'
 import json, sys
