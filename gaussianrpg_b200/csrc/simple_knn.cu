@@ -120,7 +120,7 @@ __device__ __forceinline__ float box_dist2(const Box& b, float x, float y, float
 // insert into the ascending triple (simple_knn.cu:127-141); the distance is the reference build's contraction
 __device__ __forceinline__ void consider(float x, float y, float z, const float4 q, float (&best)[3]) {
     const float dx = __fadd_rn(q.x, -x), dy = __fadd_rn(q.y, -y), dz = __fadd_rn(q.z, -z);
-    float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));  // a*b + c*d contracts to fma(a, b, c*d)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         if (best[j] > d) { const float t = best[j]; best[j] = d; d = t; }

@@ -148,12 +148,12 @@ class _PeerFrame:
 
 
 FUSED_FORWARD_GATHER = True  # set False to force the NCCL all-gather path
-# gradients="shard": the records are reduce-scattered with NCCL (dense [P,12] buffer).  GRPG_SPARSE_EXCHANGE=1 selects the
-# sparse alternative -- only the records of the Gaussians that touch the rank's rows travel, by peer stores into the
-# owner's inbox (grpg_exchange_pack / _accumulate).  Measured on 2xB200 (2 M Gaussians): 0.135 + 0.086 ms for pack +
-# accumulate against 0.143 ms for the NCCL reduce-scatter (step 1.499 vs 1.430 ms), so NCCL is the default.
+# gradients="shard": only the records of the Gaussians that touch the rank's rows travel, by coalesced peer stores into the
+# owner's inbox (grpg_exchange_pack / _accumulate); GRPG_SPARSE_EXCHANGE=0 selects an NCCL reduce-scatter of the dense
+# [P,12] buffer instead.  Measured on 2xB200 (2 M Gaussians, every Gaussian touches both ranks' rows -- the worst case for
+# the sparse form): pack 0.078 + accumulate 0.047 ms against 0.140 ms for the reduce-scatter; step 1.403 vs 1.427 ms.
 import os as _os
-SPARSE_RECORD_EXCHANGE = _os.environ.get("GRPG_SPARSE_EXCHANGE", "0") != "0"
+SPARSE_RECORD_EXCHANGE = _os.environ.get("GRPG_SPARSE_EXCHANGE", "1") != "0"
 
 
 class _PeerInbox:

