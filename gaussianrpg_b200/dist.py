@@ -503,6 +503,9 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
         _p = _dbg.parse_buffers(P, raw[0], W, raw[1].shape[1], raw[6], raw[7], raw[8])
         band_parsed_R, band_R_ref = _p["num_binned"], raw[0]
         band_V = int((_p["tiles_touched"] != 0).sum())
+        _lens = (_p["ranges"][:, 1] - _p["ranges"][:, 0]).long()
+        tile_load = {"tiles": int(_lens.numel()), "mean_instances": float(_lens.float().mean()),
+                     "max_instances": int(_lens.max()), "p99_instances": int(_lens.float().quantile(0.99))}
         del raw, _p
     capacity = int(band_parsed_R * 1.25) + 4096
     _C.set_static_binning(capacity)
@@ -668,6 +671,8 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
                      "algorithmic_bytes_per_launch": alg[dom],
                      "note": f"rank {rank}'s share: R_band={band_R_ref} instances ({band_parsed_R} binned), V_band={band_V}"},
         "parity": parity,
+        "tile_load": dict(tile_load, note="instances per 16x16 tile of this rank's rows: a tile is blended by ONE CTA front to "
+                                          "back, so the heaviest tile bounds the blend kernels however many GPUs share the frame"),
         "camera_parallel": {"value": 1000.0 * args.steps * world / ms_solo_fb, "unit": "iters/s",
                             "fwd_fps": 1000.0 * args.steps * world / ms_solo_f, "scaling": "weak",
                             "value_with_gradient_allreduce": 1000.0 * args.steps * world / ms_ddp,
