@@ -588,15 +588,17 @@ def main():
         if dom in alg:
             per_launch_ms = kern[dom]["ms_per_step"] / max(1, kern[dom]["launches_per_step"])
             ach = alg[dom] / (per_launch_ms * 1e-3) / 1e9
-            traffic = None  # dram read+write bytes per launch from the committed ncu --set full capture
-            try:
-                for row in json.load(open(ROOT / "profiles" / "r1_ncu_summary.json")):
-                    if row["kernel"].startswith(dom):
-                        traffic = int((row["dram_read_MB"] + row["dram_write_MB"]) * 1e6)
-            except (OSError, KeyError, ValueError):
-                pass
+            traffic, traffic_src = None, None  # dram read+write bytes per launch from the committed ncu --set full captures
+            for name in ("r2_ncu_summary.json", "r2_ncu_packed_blends.json", "r1_ncu_summary.json"):
+                try:
+                    for row in json.load(open(ROOT / "profiles" / name)):
+                        if traffic is None and row["kernel"].startswith(dom):
+                            traffic = int((row["dram_read_MB"] + row["dram_write_MB"]) * 1e6)
+                            traffic_src = f"profiles/{name}: {row['kernel']}"
+                except (OSError, KeyError, ValueError):
+                    pass
             result["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                                  "frac": ach / peak, "traffic": traffic,
+                                  "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                                   "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                                   "algorithmic_bytes_per_launch": alg[dom],
                                   "note": "instruction-bound kernel (exp + ~25 FP32 ops per pixel-Gaussian pair); "
