@@ -16,7 +16,7 @@ LIB_PATH = _HERE / "libgrpg_b200.so"
 class GeomLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "total_bytes", "rec", "depth_key", "rect", "tiles_touched", "cov3d", "clamped", "sorted_idx", "offsets",
-        "scratch", "num_rendered")]
+        "scratch", "tile_mask", "num_rendered")]
 
 
 class BinningLayout(C.Structure):

@@ -9,7 +9,7 @@ namespace grpg {
 // preprocess_fwd.cu
 void launch_preprocess_fwd(const grpg_forward_args* a, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
                            Rec* rec, uint32_t* depth_key, uint2* rect, uint32_t* tiles_touched, float* cov3d,
-                           uint8_t* clamped, unsigned long long* ref_instances, cudaStream_t stream);
+                           uint8_t* clamped, uint32_t* tile_mask, unsigned long long* ref_instances, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
 void launch_visible_filter(int P, int W, int H, const float* means3D, const float* scales, float scale_modifier,
                            const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
@@ -23,9 +23,9 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
                               uint32_t* offsets, void* scratch, unsigned long long* counts, unsigned long long capacity,
                               int num_sms, cudaStream_t stream);
 void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tiles, const uint32_t* sorted_idx,
-                          const uint32_t* offsets, const uint2* rect, const void* geom_scratch, uint32_t* tile_keys,
-                          uint32_t* point_list, void* scratch, uint2* ranges, const unsigned long long* counts,
-                          int static_capacity, int num_sms, cudaStream_t stream);
+                          const uint32_t* offsets, const uint2* rect, const uint32_t* tile_mask, const void* geom_scratch,
+                          uint32_t* tile_keys, uint32_t* point_list, void* scratch, uint2* ranges,
+                          const unsigned long long* counts, int static_capacity, int num_sms, cudaStream_t stream);
 void launch_reference_keys(long long R, const uint32_t* point_list, const uint32_t* tile_keys, const Rec* rec,
                            unsigned long long* keys, cudaStream_t stream);
 void launch_packed_math_check(uint32_t first_bits, uint32_t last_bits, int negative, unsigned long long* out,
@@ -153,6 +153,7 @@ int grpg_get_geometry_layout(int P, grpg_geom_layout* out) {
     out->sorted_idx = take(p * 4);
     out->offsets = take(p * 4);
     out->scratch = take(geom_scratch_bytes(P));
+    out->tile_mask = take(p * 4);
     out->num_rendered = take(64);
     out->total_bytes = o;
     return 0;
@@ -215,7 +216,7 @@ static int launch_forward_geometry(const grpg_forward_args* a, unsigned long lon
     unsigned long long* ref_instances = prepare_geometry_scratch(a->P, g + L.scratch, stream);
     launch_preprocess_fwd(a, focal_x, focal_y, gx, gy, (Rec*)(g + L.rec), (uint32_t*)(g + L.depth_key),
                           (uint2*)(g + L.rect), (uint32_t*)(g + L.tiles_touched), (float*)(g + L.cov3d),
-                          (uint8_t*)(g + L.clamped), ref_instances, stream);
+                          (uint8_t*)(g + L.clamped), (uint32_t*)(g + L.tile_mask), ref_instances, stream);
     if (a->debug) if (int rc = check_cuda("preprocess", true, stream)) return rc;
     run_depth_order_and_scan(a->P, (uint32_t*)(g + L.depth_key), (uint32_t*)(g + L.sorted_idx),
                              (const uint32_t*)(g + L.tiles_touched), (uint32_t*)(g + L.offsets), g + L.scratch,
@@ -258,7 +259,8 @@ static int forward_render_impl(const grpg_forward_args* a, long long num_rendere
     char* g = (char*)a->geom_ws;
     char* b = (char*)a->binning_ws;
     run_instance_binning(a->P, num_rendered, gx, gx * gy, (const uint32_t*)(g + L.sorted_idx),
-                         (const uint32_t*)(g + L.offsets), (const uint2*)(g + L.rect), g + L.scratch,
+                         (const uint32_t*)(g + L.offsets), (const uint2*)(g + L.rect), (const uint32_t*)(g + L.tile_mask),
+                         g + L.scratch,
                          b ? (uint32_t*)(b + BL.tile_keys) : nullptr, b ? (uint32_t*)(b + BL.point_list) : nullptr,
                          b ? b + BL.scratch : nullptr, (uint2*)(im + IL.ranges),
                          (const unsigned long long*)(g + L.num_rendered), static_capacity, device_sm_count(), stream);

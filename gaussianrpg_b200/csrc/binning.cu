@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
 __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __restrict__ sorted_idx,
                                                              const uint32_t* __restrict__ offsets,
                                                              const uint2* __restrict__ rect,
+                                                             const uint32_t* __restrict__ tile_mask,
                                                              const uint32_t* __restrict__ chunk_start, uint32_t P,
                                                              uint32_t R, const unsigned long long* __restrict__ counts,
                                                              uint32_t grid_x,
@@ -153,14 +154,17 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __r
     uint32_t pos = lo64 < R ? chunk_start[chunk] : P;
     while (cur < hi && pos < P) {
         const uint32_t p = pos + lane;
-        uint32_t g = 0, off = 0xFFFFFFFFu, x0 = 0, y0 = 0, w = 1, end = 0;
+        uint32_t g = 0, off = 0xFFFFFFFFu, x0 = 0, y0 = 0, w = 1, end = 0, mask = 0xFFFFFFFFu;
         if (p < P) {
             g = sorted_idx[p];
             off = offsets[p];
             const uint2 r = rect[g];
             x0 = r.x & 0xffffu; y0 = r.y & 0xffffu;
             w = (r.x >> 16) - x0;
-            end = off + w * ((r.y >> 16) - y0);
+            const uint32_t area = w * ((r.y >> 16) - y0);
+            // rectangles of <= 32 tiles carry a mask of the tiles that can hold a visible pixel: only those are binned
+            mask = area <= 32u ? tile_mask[g] : 0xFFFFFFFFu;
+            end = off + (mask != 0xFFFFFFFFu ? (uint32_t)__popc(mask) : area);
             if (w == 0) w = 1;
         }
         const uint32_t group_end = __reduce_max_sync(0xffffffffu, end);
@@ -178,8 +182,14 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __r
             const uint32_t o_x0 = __shfl_sync(0xffffffffu, x0, owner);
             const uint32_t o_y0 = __shfl_sync(0xffffffffu, y0, owner);
             const uint32_t o_g = __shfl_sync(0xffffffffu, g, owner);
+            const uint32_t o_mask = __shfl_sync(0xffffffffu, mask, owner);
             if (k < stop) {
-                const uint32_t m = k - o_off;
+                uint32_t m = k - o_off;
+                if (o_mask != 0xFFFFFFFFu) {  // position of the (m+1)-th binned tile of the rectangle
+                    uint32_t bits = o_mask;
+                    for (uint32_t s_ = 0; s_ < m; ++s_) bits &= bits - 1u;
+                    m = (uint32_t)__ffs(bits) - 1u;
+                }
                 const uint32_t ty = m / o_w, tx = m - ty * o_w;
                 const uint32_t tile_id = (o_y0 + ty) * grid_x + (o_x0 + tx);
                 inst_tile[k] = tile_id;
@@ -309,9 +319,9 @@ void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, 
 // (counts_are_exact) or the capacity of the binning workspace in static-capacity mode, where every kernel reads the
 // count from `counts` on the device and the grids cover the capacity.
 void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tiles, const uint32_t* sorted_idx,
-                          const uint32_t* offsets, const uint2* rect, const void* geom_scratch, uint32_t* tile_keys,
-                          uint32_t* point_list, void* scratch, uint2* ranges, const unsigned long long* counts,
-                          int static_capacity, int num_sms, cudaStream_t stream) {
+                          const uint32_t* offsets, const uint2* rect, const uint32_t* tile_mask, const void* geom_scratch,
+                          uint32_t* tile_keys, uint32_t* point_list, void* scratch, uint2* ranges,
+                          const unsigned long long* counts, int static_capacity, int num_sms, cudaStream_t stream) {
     cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), stream);
     if (R <= 0) return;
     char* p = (char*)scratch;
@@ -338,7 +348,7 @@ void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tile
         static_assert(EMIT_CHUNK * 8 == 2 * SORT_TILE, "an emit CTA must cover exactly two sort tiles");
         const uint32_t sort_tiles = (uint32_t)sort_num_tiles(R);
         emit_instances_kernel<<<(sort_tiles + 1) / 2, 256, 0, stream>>>(
-            sorted_idx, offsets, rect, chunk_start, (uint32_t)P, (uint32_t)R, counts, grid_x, k0, v0,
+            sorted_idx, offsets, rect, tile_mask, chunk_start, (uint32_t)P, (uint32_t)R, counts, grid_x, k0, v0,
             sort_first_pass_hist(aux), sort_tiles, (1u << plan.bits[0]) - 1u);
     }
     onesweep_sort_pairs(k0, v0, k1, v1, R, bits, aux, num_sms, stream, "tile_sort_hist", "tile_sort_scan", "tile_sort_pass",

@@ -7,6 +7,7 @@
 // (forward.cu:74-113), computeColorFromSH (forward.cu:20-71), ndc2Pix/getRect
 // (auxiliary.h:41-56).  Rounding sequence: see DESIGN.md "arithmetic contract".
 #include <cstdio>
+#include <cstdlib>
 #include "grpg_common.cuh"
 
 namespace grpg {
@@ -245,7 +246,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
     int prefiltered, int row_stride, int row_phase, int forward_only, int* __restrict__ radii, Rec* __restrict__ rec, uint32_t* __restrict__ depth_key,
     uint2* __restrict__ rect, uint32_t* __restrict__ tiles_touched, float* __restrict__ cov3D_out,
-    uint8_t* __restrict__ clamped, int reference_binning, unsigned long long* __restrict__ ref_instances) {
+    uint8_t* __restrict__ clamped, int reference_binning, unsigned long long* __restrict__ ref_instances,
+    uint32_t* __restrict__ tile_mask) {
     __shared__ float s_cam[35];
     __shared__ uint32_t s_ref_count;  // instances the reference bins for this CTA's Gaussians (its num_rendered)
     if (threadIdx.x == 0) s_ref_count = 0;
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
         band_clip(o.ymin, o.ymax, ly0, ly1);
         ref_count = (o.xmax - o.xmin) * (ly1 - ly0);  // what the reference bins: getRect of the 3-sigma radius
         uint32_t bx0 = o.xmin, bx1 = o.xmax;
-        if (!reference_binning && !(hx == __int_as_float(0x7f800000))) {
+        if (reference_binning != 1 && !(hx == __int_as_float(0x7f800000))) {
             // Clip the rectangle to the tiles that hold a pixel with |dx| <= hx and |dy| <= hy: outside, alpha is
             // provably < 1/255 and the reference's blend skips the pair (forward.cu:418-426), so the instance is
             // never binned.  Images, gradients and radii are unchanged; the instance lists become the reference's
@@ -369,7 +371,25 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
             }
             band_clip(by0, by1, ly0, ly1);
         }
-        tiles_touched[idx] = (bx1 - bx0) * (ly1 - ly0);
+        uint32_t n_tiles = (bx1 - bx0) * (ly1 - ly0), mask = 0xFFFFFFFFu;
+        if (reference_binning == 0 && n_tiles > 0u && n_tiles <= 32u) {
+            // Exact per-tile culling for small rectangles: a tile is binned only if it can hold a pixel with
+            // alpha >= 1/255 -- the same conservative ellipse-vs-rectangle test the blend kernels run per 8x8 block
+            // (a block is a subset of its tile, so a tile that fails is failed by all of its blocks: the blend would
+            // discard the instance).  The surviving tiles are a bit mask over the rectangle (row-major).
+            const uint32_t w = bx1 - bx0;
+            const uint32_t st = row_stride > 1 ? (uint32_t)row_stride : 1u, ph = row_stride > 1 ? (uint32_t)row_phase : 0u;
+            mask = 0u;
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t ty_l = ly0 + t / w, tx = bx0 + t % w;
+                const float x_lo = (float)(tx * GRPG_TILE), y_lo = (float)((ty_l * st + ph) * GRPG_TILE);
+                if (footprint_hits_exact(r.a, r.b, x_lo, x_lo + (GRPG_TILE - 1), y_lo, y_lo + (GRPG_TILE - 1))) mask |= 1u << t;
+            }
+            if (mask != 0xFFFFFFFFu) n_tiles = (uint32_t)__popc(mask);
+            // (a 32-tile rectangle whose every tile survives keeps the all-ones mask, which also means "no mask")
+        }
+        tile_mask[idx] = mask;
+        tiles_touched[idx] = n_tiles;
         depth_key[idx] = __float_as_uint(o.depth);
         rect[idx] = make_uint2(bx0 | (bx1 << 16), ly0 | (ly1 << 16));
     }
@@ -443,14 +463,22 @@ __global__ void __launch_bounds__(256) visible_filter_kernel(
 
 void launch_preprocess_fwd(const grpg_forward_args* a, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
                            Rec* rec, uint32_t* depth_key, uint2* rect, uint32_t* tiles_touched, float* cov3d,
-                           uint8_t* clamped, unsigned long long* ref_instances, cudaStream_t stream) {
+                           uint8_t* clamped, uint32_t* tile_mask, unsigned long long* ref_instances, cudaStream_t stream) {
     const int P = a->P;
+    // binning mode of the kernel: 1 = the reference's rectangles, 0 = clipped rectangles + per-tile mask (default),
+    // 2 = clipped rectangles only (GRPG_EXACT_TILE_CULL=0, kept for A/B measurements)
+    static int exact_cull = -1;
+    if (exact_cull < 0) {
+        const char* e = getenv("GRPG_EXACT_TILE_CULL");
+        exact_cull = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const int binning_mode = a->reference_binning ? 1 : (exact_cull ? 0 : 2);
     ProfScope ps("preprocess_fwd", stream);
     preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs, a->cov3D_precomp,
         a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos, a->width, a->height, a->tan_fovx, a->tan_fovy,
         focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->tile_row_stride, a->tile_row_phase, a->forward_only, a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped,
-        a->reference_binning, ref_instances);
+        binning_mode, ref_instances, tile_mask);
 }
 
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream) {

@@ -43,6 +43,7 @@ def parse_buffers(P: int, R: int, W: int, H: int, geom: torch.Tensor, binning: t
         # depth order of the Gaussians that emit instances (tiles_touched != 0): the first n_sorted entries
         sorted_idx=_view(geom, gl.sorted_idx, P, torch.int32)[:n_sorted],
         offsets=_view(geom, gl.offsets, P, torch.int32)[:n_sorted],
+        tile_mask=_view(geom, gl.tile_mask, P, torch.int32),
         rect_min=torch.stack([rect[:, 0] & 0xFFFF, rect[:, 1] & 0xFFFF], 1),
         rect_max=torch.stack([(rect[:, 0] >> 16) & 0xFFFF, (rect[:, 1] >> 16) & 0xFFFF], 1),
         n_contrib=_view(img, il.n_contrib, W * H, torch.int32).view(H, W),

@@ -46,6 +46,8 @@ typedef struct grpg_geom_layout {
     size_t sorted_idx;     /* uint32[P]: Gaussian ids ordered by (depth bits, id)           */
     size_t offsets;        /* uint32[P]: exclusive scan of tiles_touched in sorted order    */
     size_t scratch;        /* sort ping-pong buffers, histograms, look-back state           */
+    size_t tile_mask;      /* uint32[P]: for binned rectangles of <= 32 tiles, bit (ty - y0) * w + (tx - x0) is set when the
+                            * tile can hold a pixel with alpha >= 1/255 (only those tiles are binned); all ones otherwise */
     size_t num_rendered;   /* uint64[4] device counters: num_binned, num_rendered (the reference's), overflow flag of
                             * the static-capacity mode, Gaussians in the depth order (those with tiles_touched != 0) */
 } grpg_geom_layout;
