@@ -145,8 +145,9 @@ class Arm:
             rotations=out.rotation)
         return color, radii, means2D
 
-    def iteration(self, cam, gt, step_optimizer=True, densify_seed=None):
-        """One training iteration; `densify_seed` not None = this iteration densifies and prunes (train.py:283-291)."""
+    def iteration(self, cam, gt, step_optimizer=True, densify_seed=None, forced=None):
+        """One training iteration; `densify_seed` not None = this iteration densifies and prunes (train.py:283-291).
+        `forced` = the other arm's `last_masks` (lock-step runs, see densify_and_prune)."""
         color, radii, means2D = self.render(cam)
         lam = self.cfg["lambda_dssim"]
         loss = loss_utils.l1_ssim_loss(color, gt, lam) if self.name == "ours" else self.torch_loss(color, gt, lam)
@@ -164,7 +165,7 @@ class Arm:
                 s[2][vis] += 1
                 off += n
         if densify_seed is not None:
-            self.densify_and_prune(densify_seed)
+            self.densify_and_prune(densify_seed, forced)
         if step_optimizer:
             if self.name == "ours":
                 optim.fused_adam_step(self.opts)
@@ -213,9 +214,15 @@ class Arm:
 
     # ---- gaussian_model.py:453-553 with the bkgd / actor rules -----------------------------------------------------
     @torch.no_grad()
-    def densify_and_prune(self, seed):
+    def densify_and_prune(self, seed, forced=None):
+        """Every sub-model's clone / split / prune decisions are computed from THIS arm's statistics and parameters
+        and kept in `last_masks`.  With `forced` (the `last_masks` of the other arm of a lock-step run, which holds the
+        same point set) the other arm's decisions are the ones applied, and the report counts the Gaussians on which
+        the two arms decided differently (`disagree`): the arms then keep identical point sets through every event, so
+        their trajectories stay comparable iteration by iteration instead of drifting apart after the first
+        borderline Gaussian."""
         c = self.cfg
-        report = []
+        report, masks = [], []
         for k in range(len(self.subs)):
             p = self.subs[k]
             if self.is_bkgd[k]:
@@ -229,6 +236,9 @@ class Arm:
             n0 = p["xyz"].shape[0]
             # clone (:501-528)
             sel = (torch.norm(grads, dim=-1) >= max_grad) & (torch.exp(p["scaling"]).max(1).values <= c["percent_dense"] * extent)
+            own = dict(clone=sel)
+            if forced is not None:
+                sel = forced[k]["clone"]
             n_clone = int(sel.sum())
             self._cat_points(k, {n: p[n][sel] for n in PARAMS})
             p = self.subs[k]
@@ -237,6 +247,9 @@ class Arm:
             padded = torch.zeros(n_init, device=self.dev)
             padded[:grads.shape[0]] = grads.squeeze(1)
             sel = (padded >= max_grad) & (torch.exp(p["scaling"]).max(1).values > c["percent_dense"] * extent)
+            own["split"] = sel
+            if forced is not None:
+                sel = forced[k]["split"]
             n_split = int(sel.sum())
             gen = torch.Generator(device=self.dev)
             gen.manual_seed(int(seed) * 1000 + k)
@@ -253,13 +266,18 @@ class Arm:
             p = self.subs[k]
             # prune (:540-547; prune_big_points is False before opacity_reset_interval, train.py:281)
             prune = (torch.sigmoid(p["opacity"]) < c["min_opacity"]).squeeze(1)
+            own["prune"] = prune
+            if forced is not None:
+                prune = forced[k]["prune"]
             n_prune = int(prune.sum())
             self._prune_points(k, ~prune)
             n1 = self.subs[k]["xyz"].shape[0]
             self.stats[k] = [torch.zeros(n1, device=self.dev), torch.zeros(n1, 2, device=self.dev),
                              torch.zeros(n1, 1, device=self.dev)]
-            report.append(dict(before=n0, cloned=n_clone, split=n_split, pruned=n_prune, after=n1))
-        self.last_densify = report
+            disagree = 0 if forced is None else sum(int((own[m] != forced[k][m]).sum()) for m in ("clone", "split", "prune"))
+            report.append(dict(before=n0, cloned=n_clone, split=n_split, pruned=n_prune, after=n1, disagree=disagree))
+            masks.append(own)
+        self.last_densify, self.last_masks = report, masks
         return report
 
 
@@ -307,4 +325,27 @@ def run_training(arm: Arm, iters, densify_at, cam_order=None, eval_cam=0, eval_a
         e1.record()
         torch.cuda.synchronize()
         out["ms_per_iter"] = e0.elapsed_time(e1) / (iters - time_from + 1)
+    return out
+
+
+def run_training_lockstep(leader: Arm, follower: Arm, iters, densify_at, eval_cam=0, eval_at=()):
+    """Both arms step through the same iterations side by side.  At a densify event each arm computes its own
+    clone / split / prune decisions; the leader's are applied in both (Arm.densify_and_prune, `forced`), and the number
+    of Gaussians the follower would have decided differently is recorded.  Returns {arm.name: dict(losses, sizes,
+    renders)}; `sizes[it]` of the follower carries `disagree` per sub-model."""
+    n_cams = len(leader.cams.scenes)
+    out = {a.name: dict(losses=[], sizes={}, renders={}) for a in (leader, follower)}
+    for it in range(1, iters + 1):
+        cam = (it - 1) % n_cams
+        seed = it if it in densify_at else None
+        for arm in (leader, follower):
+            forced = leader.last_masks if (seed is not None and arm is follower) else None
+            loss = arm.iteration(cam, arm.cams.gt[cam], densify_seed=seed, forced=forced)
+            o = out[arm.name]
+            o["losses"].append(float(loss.item()))
+            if seed is not None:
+                o["sizes"][it] = (arm.sizes(), arm.last_densify)
+            if it in eval_at:
+                with torch.no_grad():
+                    o["renders"][it] = arm.render(eval_cam)[0].detach().clone()
     return out
