@@ -119,6 +119,21 @@ __global__ void __launch_bounds__(256) scan_tiles_kernel(const uint32_t* __restr
     }
 }
 
+// position of the (n+1)-th set bit of `mask` (n < popc(mask)): five popc steps, no data-dependent loop
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t n) {
+    uint32_t pos = 0;
+    uint32_t c = (uint32_t)__popc(mask & 0xFFFFu);
+    if (n >= c) { pos = 16; n -= c; }
+    c = (uint32_t)__popc((mask >> pos) & 0xFFu);
+    if (n >= c) { pos += 8; n -= c; }
+    c = (uint32_t)__popc((mask >> pos) & 0xFu);
+    if (n >= c) { pos += 4; n -= c; }
+    c = (uint32_t)__popc((mask >> pos) & 0x3u);
+    if (n >= c) { pos += 2; n -= c; }
+    if (n >= ((mask >> pos) & 1u)) pos += 1;
+    return pos;
+}
+
 // ---- 3. instance emission ------------------------------------------------------------------
 // Output-balanced: warp k writes instances [k*EMIT_CHUNK, (k+1)*EMIT_CHUNK) no matter how they are
 // distributed over Gaussians (a splat covering the whole screen is shared by many warps; the
@@ -185,12 +200,19 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const uint32_t* __r
             const uint32_t o_mask = __shfl_sync(0xffffffffu, mask, owner);
             if (k < stop) {
                 uint32_t m = k - o_off;
-                if (o_mask != 0xFFFFFFFFu) {  // position of the (m+1)-th binned tile of the rectangle
-                    uint32_t bits = o_mask;
-                    for (uint32_t s_ = 0; s_ < m; ++s_) bits &= bits - 1u;
-                    m = (uint32_t)__ffs(bits) - 1u;
+                if (o_mask != 0xFFFFFFFFu) m = nth_set_bit(o_mask, m);  // the (m+1)-th binned tile of the rectangle
+                // m / o_w through a float estimate and one correction step (exact below 2^22; a 32-bit integer
+                // division costs ~20 instructions per instance)
+                uint32_t ty;
+                if (m < (1u << 22)) {
+                    ty = (uint32_t)((float)m * __frcp_rn((float)o_w));
+                    const int rem = (int)(m - ty * o_w);
+                    if (rem < 0) --ty;
+                    else if (rem >= (int)o_w) ++ty;
+                } else {
+                    ty = m / o_w;
                 }
-                const uint32_t ty = m / o_w, tx = m - ty * o_w;
+                const uint32_t tx = m - ty * o_w;
                 const uint32_t tile_id = (o_y0 + ty) * grid_x + (o_x0 + tx);
                 inst_tile[k] = tile_id;
                 inst_gauss[k] = o_g;

@@ -534,8 +534,12 @@ __global__ void __launch_bounds__(128, MINB) blend_bwd_packed_kernel(
 
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     const int red_sub = ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-    const int red_slot = red_sub < 3 ? ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + red_sub : 11;
-    const float slot_scale = red_slot == 0 ? -ddelx_dx : red_slot == 1 ? -ddely_dy : (red_slot >= 3 && red_slot <= 5) ? -0.5f : 1.0f;
+    const int red_slot = red_sub < 3 ? ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + red_sub : 12;  // 12 = pad lane
+    // Slots 2 and 11 carry sum |px_| and sum |py_|: both go to record component 2 (the |gx| + |gy| channel), scaled by
+    // 0.5 W and 0.5 H here -- once per (warp, Gaussian) instead of two packed multiplies per lane.
+    const float slot_scale = red_slot == 0 ? -ddelx_dx : red_slot == 1 ? -ddely_dy : red_slot == 2 ? ddelx_dx :
+                             red_slot == 11 ? ddely_dy : (red_slot >= 3 && red_slot <= 5) ? -0.5f : 1.0f;
+    const int red_comp = red_slot == 11 ? 2 : red_slot;
 
     const int wmax = __reduce_max_sync(0xffffffffu, max(last0, last1));
     if (lane == 0) s_maxlast[warp] = wmax;
@@ -640,13 +644,12 @@ __global__ void __launch_bounds__(128, MINB) blend_bwd_packed_kernel(
             const float2 u = fmul2(uG, f2(dx)), v = fmul2(uG, dy);
             const float2 px_ = ffma2(u, f2(b.x), fmul2(v, f2(b.y)));
             const float2 py_ = ffma2(v, f2(b.z), fmul2(u, f2(b.y)));
-            const float2 ab = ffma2(f2(fabsf(py_.x), fabsf(py_.y)), f2(ddely_dy), fmul2(f2(fabsf(px_.x), fabsf(px_.y)), f2(ddelx_dx)));
             const float2 udy = fmul2(u, dy), vdy = fmul2(v, dy), gd = fmul2(Ge, dLo);
             const float2 w0 = fmul2(w_at, dp0), w1 = fmul2(w_at, dp1), w2 = fmul2(w_at, dp2), wd = fmul2(w_at, dpd);
             float vals[12];
             vals[0] = px_.x + px_.y;
             vals[1] = py_.x + py_.y;
-            vals[2] = ab.x + ab.y;
+            vals[2] = fabsf(px_.x) + fabsf(px_.y);
             vals[3] = (u.x + u.y) * dx;
             vals[4] = udy.x + udy.y;
             vals[5] = vdy.x + vdy.y;
@@ -655,9 +658,211 @@ __global__ void __launch_bounds__(128, MINB) blend_bwd_packed_kernel(
             vals[8] = w1.x + w1.y;
             vals[9] = w2.x + w2.y;
             vals[10] = wd.x + wd.y;
-            vals[11] = 0.f;
+            vals[11] = fabsf(py_.x) + fabsf(py_.y);
             const float mine = warp_reduce12_packed(vals, lane) * slot_scale;
-            if (!(lane & 1) && red_slot < 11) atomicAdd(grad_rec + (size_t)gid * GREC + red_slot, mine);
+            if (!(lane & 1) && red_slot < 12) atomicAdd(grad_rec + (size_t)gid * GREC + red_comp, mine);
+        }
+    }
+    cp_async_wait_all();
+}
+
+// ---- batched ("pipelined") variant of the packed kernel -------------------------------------------------------------
+// Same arithmetic per pixel.  The packed kernel above runs every queue entry as one serial chain (loads -> power ->
+// vote -> expf -> vote -> recurrence -> 5-level butterfly -> RED), several hundred cycles that only other warps can
+// hide; a tile-row band of a sharded frame lasts as long as its heaviest tile, whose warps end up alone on their SM
+// (DESIGN section 8).  Here NB queue entries are taken at a time: the state-independent part (loads, power, expf,
+// alpha: "stage P") is issued for all NB as straight-line code, then the recurrences and the butterflies of the NB
+// entries follow in one basic block, so the butterfly of one entry overlaps the chain of the next.  Entries whose
+// pixels all turn out inactive are not skipped (they add exact zeros and issue no RED).
+template <int MINB, int NB>
+__global__ void __launch_bounds__(128, MINB) blend_bwd_pipe_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const Rec* __restrict__ rec, int W, int H,
+    const float* __restrict__ bg_color, const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
+    const float* __restrict__ dL_dalphas, float* __restrict__ grad_rec /*[P][12]*/, int HL, int row_stride,
+    int row_phase, int grads_full) {
+    constexpr int NT = 128, NW = 4, RPT = BWD_BATCH / NT;
+    __shared__ __align__(16) float4 s_rec2[2][BWD_BATCH * 3];
+    __shared__ uint32_t s_id2[2][BWD_BATCH];
+    __shared__ int s_maxlast[NW];
+    __shared__ uint16_t s_q[NW][BWD_BATCH];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
+    const uint32_t tile = blockIdx.y * tiles_x + blockIdx.x;
+    const int bx0 = blockIdx.x * GRPG_TILE + (warp & 1) * 8;
+    const int wy0 = (warp >> 1) * 8;
+    const int by0 = (blockIdx.y * row_stride + row_phase) * GRPG_TILE + wy0;
+    const int pix_x = bx0 + (lane & 7);
+    const int row0 = by0 + 2 * (lane >> 3);
+    const float pxf = (float)pix_x;
+    const float2 npy = f2(-(float)row0, -(float)(row0 + 1));
+    const float bx_lo = (float)bx0, bx_hi = (float)(bx0 + 7), by_lo = (float)by0, by_hi = (float)(by0 + 7);
+    const size_t hw = grads_full ? (size_t)H * W : (size_t)HL * W;
+
+    const uint2 range = ranges[tile];
+    const int n_inst = (int)(range.y - range.x);
+    const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
+
+    float sT[2], sL[2], sd0[2], sd1[2], sd2[2], sdd[2], sda[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int pix_y = row0 + p;
+        const int loc_y = blockIdx.y * GRPG_TILE + wy0 + 2 * (lane >> 3) + p;
+        const bool inside = pix_x < W && pix_y < H;
+        const size_t pid = (size_t)loc_y * W + pix_x;
+        const size_t gpx = grads_full ? (size_t)pix_y * W + pix_x : pid;
+        sT[p] = inside ? 1.0f - alphas[pid] : 0.0f;  // T_final (backward.cu:468)
+        sL[p] = inside ? __uint_as_float(n_contrib[pid]) : 0.0f;
+        sd0[p] = inside ? dL_dpixels[gpx] : 0.f;
+        sd1[p] = inside ? dL_dpixels[hw + gpx] : 0.f;
+        sd2[p] = inside ? dL_dpixels[2 * hw + gpx] : 0.f;
+        sdd[p] = inside ? dL_dpixel_depths[gpx] : 0.f;
+        sda[p] = inside ? dL_dalphas[gpx] : 0.f;
+    }
+    float2 T = f2(sT[0], sT[1]);
+    const float2 dp0 = f2(sd0[0], sd0[1]), dp1 = f2(sd1[0], sd1[1]), dp2 = f2(sd2[0], sd2[1]);
+    const float2 dpd = f2(sdd[0], sdd[1]), dpa = f2(sda[0], sda[1]);
+    const float2 ntfb = f2(-(sT[0] * (bg0 * sd0[0] + bg1 * sd1[0] + bg2 * sd2[0])),
+                           -(sT[1] * (bg0 * sd0[1] + bg1 * sd1[1] + bg2 * sd2[1])));
+    const int last0 = (int)__float_as_uint(sL[0]), last1 = (int)__float_as_uint(sL[1]);
+    float2 accA = f2(0.f);
+
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    const int red_sub = ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const int red_slot = red_sub < 3 ? ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + red_sub : 12;  // 12 = pad lane
+    const float slot_scale = red_slot == 0 ? -ddelx_dx : red_slot == 1 ? -ddely_dy : red_slot == 2 ? ddelx_dx :
+                             red_slot == 11 ? ddely_dy : (red_slot >= 3 && red_slot <= 5) ? -0.5f : 1.0f;
+    const int red_comp = red_slot == 11 ? 2 : red_slot;
+    const bool red_lane = !(lane & 1) && red_slot < 12;
+
+    const int wmax = __reduce_max_sync(0xffffffffu, max(last0, last1));
+    if (lane == 0) s_maxlast[warp] = wmax;
+    __syncthreads();
+    int tile_last = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) tile_last = max(tile_last, s_maxlast[w]);
+    tile_last = min(tile_last, n_inst);
+
+    auto stage = [&](int buf, int top, const uint32_t (&id)[RPT]) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int t = tid + r * NT;
+            if (top - 1 - t >= 0) {
+                const float4* src = reinterpret_cast<const float4*>(rec + id[r]);
+                float4* d = &s_rec2[buf][3 * t];
+                cp_async16(d, src); cp_async16(d + 1, src + 1); cp_async16(d + 2, src + 2);
+                s_id2[buf][t] = id[r];
+            }
+        }
+        cp_async_commit();
+    };
+    auto fetch_id = [&](int top, uint32_t (&id)[RPT]) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int t = tid + r * NT;
+            id[r] = top - 1 - t >= 0 ? point_list[range.x + top - 1 - t] : 0u;
+        }
+    };
+    uint32_t id_next[RPT];
+    fetch_id(tile_last, id_next);
+    stage(0, tile_last, id_next);
+    fetch_id(tile_last - BWD_BATCH, id_next);
+
+    for (int top = tile_last, it = 0; top > 0; top -= BWD_BATCH, ++it) {
+        const int cnt = min(BWD_BATCH, top);
+        cp_async_wait_all();
+        __syncthreads();
+        const float4* s_rec = s_rec2[it & 1];
+        const uint32_t* s_id = s_id2[it & 1];
+        stage((it + 1) & 1, top - BWD_BATCH, id_next);
+        fetch_id(top - 2 * BWD_BATCH, id_next);
+        if (wmax <= top - cnt) continue;
+
+        uint16_t* q = s_q[warp];
+        const char* rec_base = reinterpret_cast<const char*>(s_rec);
+        int n_q = 0;
+        for (int g0 = 0; g0 < cnt; g0 += 32) {
+            const int j = g0 + lane;
+            const bool hit = j < cnt && (top - 1 - j) < wmax &&
+                             footprint_hits_exact(s_rec[3 * j], s_rec[3 * j + 1], bx_lo, bx_hi, by_lo, by_hi);
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) q[n_q + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+            n_q += __popc(m);
+        }
+        __syncwarp();
+        for (int i0 = 0; i0 < n_q; i0 += NB) {
+            // stage P (state-independent).  A slot past the end of the queue replays the last entry, inactive.
+            float2 ae[NB], Ge[NB], dy[NB];
+            float dx[NB];
+            float4 b[NB], c[NB];
+            uint32_t gid[NB];
+            bool any_active[NB];
+#pragma unroll
+            for (int e = 0; e < NB; ++e) {
+                const bool valid = i0 + e < n_q;
+                const int k = (int)q[valid ? i0 + e : n_q - 1];
+                const float4* rk = reinterpret_cast<const float4*>(rec_base + (uint32_t)k * 48u);
+                const int pos = top - 1 - k;
+                const float4 a = rk[0];
+                b[e] = rk[1];
+                c[e] = rk[2];
+                gid[e] = s_id[k];
+                dx[e] = fadd(-pxf, a.x);
+                dy[e] = fadd2(f2(a.y), npy);
+                const float2 dxAB = fmul2(f2(dx[e]), f2(b[e].x, b[e].y));
+                const float2 tc = fmul2(dy[e], fmul2(dy[e], f2(b[e].z)));
+                const float2 tb = fmul2(dy[e], f2(dxAB.y));
+                const float2 power = ffma2(ffma2(f2(dx[e]), f2(dxAB.x), tc), f2(-0.5f), f2(-tb.x, -tb.y));
+                const bool mb0 = valid && (pos < last0) && !(power.x > 0.0f) && !(power.x < a.w);
+                const bool mb1 = valid && (pos < last1) && !(power.y > 0.0f) && !(power.y < a.w);
+                const float2 G = expf2_exact(power);
+                float2 al = fmul2(f2(b[e].w), G);
+                al = f2(fminf(0.99f, al.x), fminf(0.99f, al.y));
+                const bool ac0 = mb0 && (al.x >= 1.0f / 255.0f), ac1 = mb1 && (al.y >= 1.0f / 255.0f);
+                ae[e] = f2(ac0 ? al.x : 0.0f, ac1 ? al.y : 0.0f);
+                Ge[e] = f2(ac0 ? G.x : 0.0f, ac1 ? G.y : 0.0f);
+                any_active[e] = __any_sync(0xffffffffu, ac0 || ac1);
+            }
+            // stage B: recurrence + reduction, entry by entry (back to front), one basic block
+#pragma unroll
+            for (int e = 0; e < NB; ++e) {
+                const float2 om = fadd2(f2(-ae[e].x, -ae[e].y), f2(1.0f));
+                float2 inv;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(om.x));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(om.y));
+                T = fmul2(T, inv);
+                const float2 w_at = fmul2(ae[e], T);
+                float2 s_k = ffma2(f2(c[e].x), dp0, dpa);
+                s_k = ffma2(f2(c[e].y), dp1, s_k);
+                s_k = ffma2(f2(c[e].z), dp2, s_k);
+                s_k = ffma2(f2(c[e].w), dpd, s_k);
+                float2 dLo = fmul2(fadd2(s_k, f2(-accA.x, -accA.y)), T);
+                dLo = ffma2(ntfb, inv, dLo);
+                accA = ffma2(ae[e], s_k, fmul2(om, accA));  // for the next (nearer) Gaussian
+
+                const float2 uG = fmul2(fmul2(f2(b[e].w), dLo), Ge[e]);
+                const float2 u = fmul2(uG, f2(dx[e])), v = fmul2(uG, dy[e]);
+                const float2 px_ = ffma2(u, f2(b[e].x), fmul2(v, f2(b[e].y)));
+                const float2 py_ = ffma2(v, f2(b[e].z), fmul2(u, f2(b[e].y)));
+                const float2 udy = fmul2(u, dy[e]), vdy = fmul2(v, dy[e]), gd = fmul2(Ge[e], dLo);
+                const float2 w0 = fmul2(w_at, dp0), w1 = fmul2(w_at, dp1), w2 = fmul2(w_at, dp2), wd = fmul2(w_at, dpd);
+                float vals[12];
+                vals[0] = px_.x + px_.y;
+                vals[1] = py_.x + py_.y;
+                vals[2] = fabsf(px_.x) + fabsf(px_.y);
+                vals[3] = (u.x + u.y) * dx[e];
+                vals[4] = udy.x + udy.y;
+                vals[5] = vdy.x + vdy.y;
+                vals[6] = gd.x + gd.y;
+                vals[7] = w0.x + w0.y;
+                vals[8] = w1.x + w1.y;
+                vals[9] = w2.x + w2.y;
+                vals[10] = wd.x + wd.y;
+                vals[11] = fabsf(py_.x) + fabsf(py_.y);
+                const float mine = warp_reduce12_packed(vals, lane) * slot_scale;
+                if (red_lane && any_active[e]) atomicAdd(grad_rec + (size_t)gid[e] * GREC + red_comp, mine);
+            }
         }
     }
     cp_async_wait_all();
@@ -670,6 +875,26 @@ static int bwd_pixels_per_lane() {
         const char* e = getenv("GRPG_BWD_PPL");
         v = e ? atoi(e) : GRPG_BWD_PPL_DEFAULT;
         if (v != 1 && v != 2 && v != 3) v = GRPG_BWD_PPL_DEFAULT;
+    }
+    return v;
+}
+// GRPG_BWD_PIPE: 0 = blend_bwd_packed_kernel always, 1 = the batched kernel always, 2 = the batched kernel for
+// tile-row bands only (sharded frames); GRPG_BWD_PIPE_CFG = "<min blocks><entries per batch>" (42, 52, 62, 44)
+#define GRPG_BWD_PIPE_DEFAULT 0
+#define GRPG_BWD_PIPE_CFG_DEFAULT 52
+static int bwd_pipe_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GRPG_BWD_PIPE");
+        v = e ? atoi(e) : GRPG_BWD_PIPE_DEFAULT;
+    }
+    return v;
+}
+static int bwd_pipe_cfg() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GRPG_BWD_PIPE_CFG");
+        v = e ? atoi(e) : GRPG_BWD_PIPE_CFG_DEFAULT;
     }
     return v;
 }
@@ -704,7 +929,19 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
     blend_bwd_packed_kernel<MINBV><<<grid, 128, 0, stream>>>(ranges, point_list, rec, a->width, a->height, a->background, \
                                                              a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth,      \
                                                              a->dL_dalphas, grad_rec, HL, stride, phase, gfull)
-    if (ppl == 3) {
+    if (ppl == 3 && (bwd_pipe_mode() == 1 || (bwd_pipe_mode() == 2 && stride > 1))) {
+#define GRPG_BWD_PIPE(MINBV, NBV)                                                                                         \
+    blend_bwd_pipe_kernel<MINBV, NBV><<<grid, 128, 0, stream>>>(ranges, point_list, rec, a->width, a->height, a->background, \
+                                                                a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth,        \
+                                                                a->dL_dalphas, grad_rec, HL, stride, phase, gfull)
+        switch (bwd_pipe_cfg()) {
+            case 42: GRPG_BWD_PIPE(4, 2); break;
+            case 62: GRPG_BWD_PIPE(6, 2); break;
+            case 44: GRPG_BWD_PIPE(4, 4); break;
+            default: GRPG_BWD_PIPE(5, 2); break;
+        }
+#undef GRPG_BWD_PIPE
+    } else if (ppl == 3) {
         const int mb = bwd_min_blocks();
         if (mb == 6) GRPG_BWD_PACKED(6);
         else if (mb == 8) GRPG_BWD_PACKED(8);

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     __shared__ __align__(16) float s_scales[256 * 3];
     __shared__ __align__(16) float s_sh[256 * 12];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmask[256];
     const int cta_first = blockIdx.x * blockDim.x;
     auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     // the ragged last CTA and 16-byte-misaligned views use plain loads
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     }
     Rec r;
     uint32_t ref_count = 0;
+    uint32_t n_tiles = 0, mask = 0xFFFFFFFFu, cull_cnt = 0, cull_w = 1, cull_x0 = 0, cull_y0 = 0;
     if (!vis) {
         radii[idx] = 0;
         tiles_touched[idx] = 0;
@@ -371,35 +373,91 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
             }
             band_clip(by0, by1, ly0, ly1);
         }
-        uint32_t n_tiles = (bx1 - bx0) * (ly1 - ly0), mask = 0xFFFFFFFFu;
+        n_tiles = (bx1 - bx0) * (ly1 - ly0);
+        cull_w = bx1 - bx0; cull_x0 = bx0; cull_y0 = ly0;
         if (reference_binning == 0 && n_tiles > 0u && n_tiles <= 32u) {
             // Exact per-tile culling for small rectangles: a tile is binned only if it can hold a pixel with
             // alpha >= 1/255 -- the same conservative ellipse-vs-rectangle test the blend kernels run per 8x8 block
             // (a block is a subset of its tile, so a tile that fails is failed by all of its blocks: the blend would
             // discard the instance).  The surviving tiles are a bit mask over the rectangle (row-major).
-            const uint32_t w = bx1 - bx0;
-            const uint32_t st = row_stride > 1 ? (uint32_t)row_stride : 1u, ph = row_stride > 1 ? (uint32_t)row_phase : 0u;
-            mask = 0u;
-            for (uint32_t t = 0; t < n_tiles; ++t) {
-                const uint32_t ty_l = ly0 + t / w, tx = bx0 + t % w;
-                const float x_lo = (float)(tx * GRPG_TILE), y_lo = (float)((ty_l * st + ph) * GRPG_TILE);
-                if (footprint_hits_exact(r.a, r.b, x_lo, x_lo + (GRPG_TILE - 1), y_lo, y_lo + (GRPG_TILE - 1))) mask |= 1u << t;
+            if (full_cta) {
+                cull_cnt = n_tiles;  // tested below, one (Gaussian, tile) pair per lane
+            } else {
+                const uint32_t st = row_stride > 1 ? (uint32_t)row_stride : 1u, ph = row_stride > 1 ? (uint32_t)row_phase : 0u;
+                mask = 0u;
+                for (uint32_t t = 0; t < n_tiles; ++t) {
+                    const uint32_t ty_l = ly0 + t / cull_w, tx = bx0 + t % cull_w;
+                    const float x_lo = (float)(tx * GRPG_TILE), y_lo = (float)((ty_l * st + ph) * GRPG_TILE);
+                    if (footprint_hits_exact(r.a, r.b, x_lo, x_lo + (GRPG_TILE - 1), y_lo, y_lo + (GRPG_TILE - 1))) mask |= 1u << t;
+                }
+                if (mask != 0xFFFFFFFFu) n_tiles = (uint32_t)__popc(mask);
+                // (a 32-tile rectangle whose every tile survives keeps the all-ones mask, which also means "no mask")
             }
-            if (mask != 0xFFFFFFFFu) n_tiles = (uint32_t)__popc(mask);
-            // (a 32-tile rectangle whose every tile survives keeps the all-ones mask, which also means "no mask")
         }
-        tile_mask[idx] = mask;
-        tiles_touched[idx] = n_tiles;
         depth_key[idx] = __float_as_uint(o.depth);
         rect[idx] = make_uint2(bx0 | (bx1 << 16), ly0 | (ly1 << 16));
+    }
+    if (full_cta) {
+        // Warp-cooperative form of the per-tile test (all 32 lanes of a full CTA are here): the (Gaussian, tile) pairs
+        // of the warp's small rectangles are numbered by a prefix sum and tested 32 at a time, one pair per lane,
+        // instead of every lane looping over its own rectangle (measured: the per-lane loop doubled this kernel,
+        // 0.104 -> 0.212 ms on the 2 M scene).  Records are read back from the slots they are stored from anyway.
+        float4* slot = reinterpret_cast<float4*>(s_sh) + 3 * threadIdx.x;
+        slot[0] = r.a; slot[1] = r.b; slot[2] = r.c;
+        const int lane = threadIdx.x & 31;
+        uint32_t incl = cull_cnt;
+#pragma unroll
+        for (int o_ = 1; o_ < 32; o_ <<= 1) {
+            const uint32_t t_ = __shfl_up_sync(0xffffffffu, incl, o_);
+            if (lane >= o_) incl += t_;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            uint32_t* wmask = s_tmask + (threadIdx.x & ~31u);
+            wmask[lane] = 0u;
+            __syncwarp();
+            const uint32_t excl = incl - cull_cnt;
+            const uint32_t st = row_stride > 1 ? (uint32_t)row_stride : 1u, ph = row_stride > 1 ? (uint32_t)row_phase : 0u;
+            for (uint32_t base = 0; base < total; base += 32) {
+                const uint32_t pr = base + lane;
+                int owner = 0;  // number of lanes whose inclusive count is <= pr = the lane that owns pair pr
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const uint32_t probe = __shfl_sync(0xffffffffu, incl, (owner + step - 1) & 31);
+                    if (probe <= pr) owner += step;
+                }
+                owner &= 31;
+                const uint32_t t = pr - __shfl_sync(0xffffffffu, excl, owner);
+                const uint32_t ow = __shfl_sync(0xffffffffu, cull_w, owner);
+                const uint32_t ox0 = __shfl_sync(0xffffffffu, cull_x0, owner);
+                const uint32_t oy0 = __shfl_sync(0xffffffffu, cull_y0, owner);
+                if (pr < total) {
+                    // t < 32 and ow <= 32: (t + 0.5) / ow is at least 1/64 away from every integer, float is exact enough
+                    const uint32_t ty = (uint32_t)(((float)t + 0.5f) * __frcp_rn((float)ow));
+                    const uint32_t tx = t - ty * ow;
+                    const float4* os = reinterpret_cast<const float4*>(s_sh) + 3 * ((threadIdx.x & ~31u) + owner);
+                    const float x_lo = (float)((ox0 + tx) * GRPG_TILE), y_lo = (float)(((oy0 + ty) * st + ph) * GRPG_TILE);
+                    if (footprint_hits_exact(os[0], os[1], x_lo, x_lo + (GRPG_TILE - 1), y_lo, y_lo + (GRPG_TILE - 1)))
+                        atomicOr(&wmask[owner], 1u << t);
+                }
+            }
+            __syncwarp();
+            if (cull_cnt) {
+                mask = wmask[lane];
+                // (a 32-tile rectangle whose every tile survives keeps the all-ones mask, which also means "no mask")
+                if (mask != 0xFFFFFFFFu) n_tiles = (uint32_t)__popc(mask);
+            }
+        }
+    }
+    if (vis) {
+        tile_mask[idx] = mask;
+        tiles_touched[idx] = n_tiles;
     }
     // The 256 records of a full CTA are one contiguous 12 KB range: each thread drops its record into its own
     // (already consumed) 48-byte SH slot and one thread writes the range back with a TMA bulk store.
     if (full_cta) {
         ref_count = __reduce_add_sync(0xffffffffu, ref_count);
         if ((threadIdx.x & 31) == 0 && ref_count) atomicAdd(&s_ref_count, ref_count);
-        float4* slot = reinterpret_cast<float4*>(s_sh) + 3 * threadIdx.x;
-        slot[0] = r.a; slot[1] = r.b; slot[2] = r.c;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 0) {
