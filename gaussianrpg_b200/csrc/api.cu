@@ -22,6 +22,7 @@ unsigned long long* prepare_geometry_scratch(int P, void* scratch, cudaStream_t 
 void run_depth_order_and_scan(int P, uint32_t* depth_key, uint32_t* sorted_idx, const uint32_t* tiles_touched,
                               uint32_t* offsets, void* scratch, unsigned long long* counts, unsigned long long capacity,
                               int num_sms, cudaStream_t stream);
+bool exact_tile_cull();  // preprocess_fwd.cu: per-tile masks are written (and read by the emission) only in that mode
 void run_instance_binning(int P, long long R, uint32_t grid_x, uint32_t num_tiles, const uint32_t* sorted_idx,
                           const uint32_t* offsets, const uint2* rect, const uint32_t* tile_mask, const void* geom_scratch,
                           uint32_t* tile_keys, uint32_t* point_list, void* scratch, uint2* ranges,
@@ -259,7 +260,8 @@ static int forward_render_impl(const grpg_forward_args* a, long long num_rendere
     char* g = (char*)a->geom_ws;
     char* b = (char*)a->binning_ws;
     run_instance_binning(a->P, num_rendered, gx, gx * gy, (const uint32_t*)(g + L.sorted_idx),
-                         (const uint32_t*)(g + L.offsets), (const uint2*)(g + L.rect), (const uint32_t*)(g + L.tile_mask),
+                         (const uint32_t*)(g + L.offsets), (const uint2*)(g + L.rect),
+                         (!a->reference_binning && exact_tile_cull()) ? (const uint32_t*)(g + L.tile_mask) : nullptr,
                          g + L.scratch,
                          b ? (uint32_t*)(b + BL.tile_keys) : nullptr, b ? (uint32_t*)(b + BL.point_list) : nullptr,
                          b ? b + BL.scratch : nullptr, (uint2*)(im + IL.ranges),

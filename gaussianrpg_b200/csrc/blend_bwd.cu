@@ -477,24 +477,27 @@ __device__ __forceinline__ float warp_reduce12_packed(const float (&v)[12], int 
 // opacity / colour / depth partials -- is issued once per lane on float2 operands.  A pixel that does not take part
 // (behind its last contributor, power > 0, alpha < 1/255) runs with alpha = 0 and G = 0: rcp(1 - 0) = 1 leaves T, the
 // recurrence keeps A (fma(0, s, 1 * A) = A) and every partial it adds is an exact zero.
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) blend_bwd_packed_kernel(
+template <int MINB, int NW = 4, int BATCH = BWD_BATCH>
+__global__ void __launch_bounds__(32 * NW, MINB) blend_bwd_packed_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const Rec* __restrict__ rec, int W, int H,
     const float* __restrict__ bg_color, const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
     const float* __restrict__ dL_dalphas, float* __restrict__ grad_rec /*[P][12]*/, int HL, int row_stride,
     int row_phase, int grads_full) {
-    constexpr int NT = 128, NW = 4, RPT = BWD_BATCH / NT;
-    __shared__ __align__(16) float4 s_rec2[2][BWD_BATCH * 3];
-    __shared__ uint32_t s_id2[2][BWD_BATCH];
+    constexpr int NT = 32 * NW, RPT = BATCH / NT;
+    static_assert(NW == 4 || NW == 1, "a CTA is a tile (4 warps) or one 8x8 block (1 warp)");
+    __shared__ __align__(16) float4 s_rec2[2][BATCH * 3];
+    __shared__ uint32_t s_id2[2][BATCH];
     __shared__ int s_maxlast[NW];
-    __shared__ uint16_t s_q[NW][BWD_BATCH];
+    __shared__ uint16_t s_q[NW][BATCH];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
-    const uint32_t tile = blockIdx.y * tiles_x + blockIdx.x;
-    const int bx0 = blockIdx.x * GRPG_TILE + (warp & 1) * 8;
-    const int wy0 = (warp >> 1) * 8;
+    const int sub = NW == 4 ? warp : (int)(blockIdx.x & 3u);  // NW == 1: one single-warp CTA per 8x8 block, see blend_fwd.cu
+    const uint32_t tile_x = NW == 4 ? blockIdx.x : (blockIdx.x >> 2);
+    const uint32_t tile = blockIdx.y * tiles_x + tile_x;
+    const int bx0 = (int)tile_x * GRPG_TILE + (sub & 1) * 8;
+    const int wy0 = (sub >> 1) * 8;
     const int by0 = (blockIdx.y * row_stride + row_phase) * GRPG_TILE + wy0;
     const int pix_x = bx0 + (lane & 7);
     const int row0 = by0 + 2 * (lane >> 3);
@@ -572,16 +575,16 @@ __global__ void __launch_bounds__(128, MINB) blend_bwd_packed_kernel(
     uint32_t id_next[RPT];
     fetch_id(tile_last, id_next);
     stage(0, tile_last, id_next);
-    fetch_id(tile_last - BWD_BATCH, id_next);
+    fetch_id(tile_last - BATCH, id_next);
 
-    for (int top = tile_last, it = 0; top > 0; top -= BWD_BATCH, ++it) {
-        const int cnt = min(BWD_BATCH, top);
+    for (int top = tile_last, it = 0; top > 0; top -= BATCH, ++it) {
+        const int cnt = min(BATCH, top);
         cp_async_wait_all();
         __syncthreads();
         const float4* s_rec = s_rec2[it & 1];
         const uint32_t* s_id = s_id2[it & 1];
-        stage((it + 1) & 1, top - BWD_BATCH, id_next);
-        fetch_id(top - 2 * BWD_BATCH, id_next);
+        stage((it + 1) & 1, top - BATCH, id_next);
+        fetch_id(top - 2 * BATCH, id_next);
         if (wmax <= top - cnt) continue;
 
         uint16_t* q = s_q[warp];
@@ -882,6 +885,7 @@ static int bwd_pixels_per_lane() {
 // tile-row bands only (sharded frames); GRPG_BWD_PIPE_CFG = "<min blocks><entries per batch>" (42, 52, 62, 44)
 #define GRPG_BWD_PIPE_DEFAULT 0
 #define GRPG_BWD_PIPE_CFG_DEFAULT 52
+int blend_split_mode();  // blend_fwd.cu
 static int bwd_pipe_mode() {
     static int v = -1;
     if (v < 0) {
@@ -941,6 +945,11 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
             default: GRPG_BWD_PIPE(5, 2); break;
         }
 #undef GRPG_BWD_PIPE
+    } else if (ppl == 3 && (blend_split_mode() == 1 || (blend_split_mode() == 2 && stride > 1))) {
+        // one single-warp CTA per 8x8 block (see blend_fwd.cu)
+        blend_bwd_packed_kernel<28, 1, 64><<<dim3(grid.x * 4, grid.y, 1), 32, 0, stream>>>(
+            ranges, point_list, rec, a->width, a->height, a->background, a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth,
+            a->dL_dalphas, grad_rec, HL, stride, phase, gfull);
     } else if (ppl == 3) {
         const int mb = bwd_min_blocks();
         if (mb == 6) GRPG_BWD_PACKED(6);

@@ -238,6 +238,7 @@ __device__ __forceinline__ void alpha_footprint(float A, float B, float C, float
     hy = __double2float_ru(ey);
 }
 
+template <bool TILE_MASK>  // per-tile culling of small rectangles (binning mode 0); false compiles it out
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales, float scale_modifier,
     const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
         }
         n_tiles = (bx1 - bx0) * (ly1 - ly0);
         cull_w = bx1 - bx0; cull_x0 = bx0; cull_y0 = ly0;
-        if (reference_binning == 0 && n_tiles > 0u && n_tiles <= 32u) {
+        if (TILE_MASK && reference_binning == 0 && n_tiles > 0u && n_tiles <= 32u) {
             // Exact per-tile culling for small rectangles: a tile is binned only if it can hold a pixel with
             // alpha >= 1/255 -- the same conservative ellipse-vs-rectangle test the blend kernels run per 8x8 block
             // (a block is a subset of its tile, so a tile that fails is failed by all of its blocks: the blend would
@@ -397,13 +398,15 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
         depth_key[idx] = __float_as_uint(o.depth);
         rect[idx] = make_uint2(bx0 | (bx1 << 16), ly0 | (ly1 << 16));
     }
-    if (full_cta) {
+    if (full_cta) {  // records go to the slots the bulk store below reads (and the per-tile test reads back)
+        float4* slot = reinterpret_cast<float4*>(s_sh) + 3 * threadIdx.x;
+        slot[0] = r.a; slot[1] = r.b; slot[2] = r.c;
+    }
+    if (TILE_MASK && full_cta) {
         // Warp-cooperative form of the per-tile test (all 32 lanes of a full CTA are here): the (Gaussian, tile) pairs
         // of the warp's small rectangles are numbered by a prefix sum and tested 32 at a time, one pair per lane,
         // instead of every lane looping over its own rectangle (measured: the per-lane loop doubled this kernel,
         // 0.104 -> 0.212 ms on the 2 M scene).  Records are read back from the slots they are stored from anyway.
-        float4* slot = reinterpret_cast<float4*>(s_sh) + 3 * threadIdx.x;
-        slot[0] = r.a; slot[1] = r.b; slot[2] = r.c;
         const int lane = threadIdx.x & 31;
         uint32_t incl = cull_cnt;
 #pragma unroll
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
         }
     }
     if (vis) {
-        tile_mask[idx] = mask;
+        if (TILE_MASK) tile_mask[idx] = mask;
         tiles_touched[idx] = n_tiles;
     }
     // The 256 records of a full CTA are one contiguous 12 KB range: each thread drops its record into its own
@@ -519,24 +522,34 @@ __global__ void __launch_bounds__(256) visible_filter_kernel(
     means2D[2 * idx + 1] = o.py;
 }
 
+// GRPG_EXACT_TILE_CULL=1: per-tile masks for small rectangles (see launch_preprocess_fwd); read once per process
+bool exact_tile_cull() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GRPG_EXACT_TILE_CULL");
+        v = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    return v != 0;
+}
+
 void launch_preprocess_fwd(const grpg_forward_args* a, float focal_x, float focal_y, uint32_t grid_x, uint32_t grid_y,
                            Rec* rec, uint32_t* depth_key, uint2* rect, uint32_t* tiles_touched, float* cov3d,
                            uint8_t* clamped, uint32_t* tile_mask, unsigned long long* ref_instances, cudaStream_t stream) {
     const int P = a->P;
-    // binning mode of the kernel: 1 = the reference's rectangles, 0 = clipped rectangles + per-tile mask (default),
-    // 2 = clipped rectangles only (GRPG_EXACT_TILE_CULL=0, kept for A/B measurements)
-    static int exact_cull = -1;
-    if (exact_cull < 0) {
-        const char* e = getenv("GRPG_EXACT_TILE_CULL");
-        exact_cull = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    const int binning_mode = a->reference_binning ? 1 : (exact_cull ? 0 : 2);
+    // binning mode of the kernel: 1 = the reference's rectangles, 2 = rectangles clipped to the alpha footprint (default),
+    // 0 = clipped rectangles + per-tile mask (GRPG_EXACT_TILE_CULL=1).  Measured on the 2 M scene:
+    // the mask removes 13 % of the binned instances and 0.037 ms from the sort and the blends, and costs 0.045 ms here
+    // plus 0.017 ms in the emission -- a net loss, so it stays an A/B switch.
+    const int binning_mode = a->reference_binning ? 1 : (exact_tile_cull() ? 0 : 2);
     ProfScope ps("preprocess_fwd", stream);
-    preprocess_fwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
-        P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs, a->cov3D_precomp,
-        a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos, a->width, a->height, a->tan_fovx, a->tan_fovy,
-        focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->tile_row_stride, a->tile_row_phase, a->forward_only, a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped,
-        binning_mode, ref_instances, tile_mask);
+#define GRPG_PRE_ARGS                                                                                                     \
+        P, a->D, a->M, a->means3D, a->scales, a->scale_modifier, a->rotations, a->opacities, a->shs, a->cov3D_precomp,   \
+        a->colors_precomp, a->viewmatrix, a->projmatrix, a->cam_pos, a->width, a->height, a->tan_fovx, a->tan_fovy,      \
+        focal_x, focal_y, grid_x, grid_y, a->prefiltered, a->tile_row_stride, a->tile_row_phase, a->forward_only,        \
+        a->radii, rec, depth_key, rect, tiles_touched, cov3d, clamped, binning_mode, ref_instances, tile_mask
+    if (binning_mode == 0) preprocess_fwd_kernel<true><<<(P + 255) / 256, 256, 0, stream>>>(GRPG_PRE_ARGS);
+    else preprocess_fwd_kernel<false><<<(P + 255) / 256, 256, 0, stream>>>(GRPG_PRE_ARGS);
+#undef GRPG_PRE_ARGS
 }
 
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream) {
