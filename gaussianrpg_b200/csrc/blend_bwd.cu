@@ -677,24 +677,26 @@ __global__ void __launch_bounds__(32 * NW, MINB) blend_bwd_packed_kernel(
 // alpha: "stage P") is issued for all NB as straight-line code, then the recurrences and the butterflies of the NB
 // entries follow in one basic block, so the butterfly of one entry overlaps the chain of the next.  Entries whose
 // pixels all turn out inactive are not skipped (they add exact zeros and issue no RED).
-template <int MINB, int NB>
-__global__ void __launch_bounds__(128, MINB) blend_bwd_pipe_kernel(
+template <int MINB, int NB, int NW = 4, int BATCH = BWD_BATCH>
+__global__ void __launch_bounds__(32 * NW, MINB) blend_bwd_pipe_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const Rec* __restrict__ rec, int W, int H,
     const float* __restrict__ bg_color, const float* __restrict__ alphas, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dpixel_depths,
     const float* __restrict__ dL_dalphas, float* __restrict__ grad_rec /*[P][12]*/, int HL, int row_stride,
     int row_phase, int grads_full) {
-    constexpr int NT = 128, NW = 4, RPT = BWD_BATCH / NT;
-    __shared__ __align__(16) float4 s_rec2[2][BWD_BATCH * 3];
-    __shared__ uint32_t s_id2[2][BWD_BATCH];
+    constexpr int NT = 32 * NW, RPT = BATCH / NT;
+    __shared__ __align__(16) float4 s_rec2[2][BATCH * 3];
+    __shared__ uint32_t s_id2[2][BATCH];
     __shared__ int s_maxlast[NW];
-    __shared__ uint16_t s_q[NW][BWD_BATCH];
+    __shared__ uint16_t s_q[NW][BATCH];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tiles_x = (W + GRPG_TILE - 1) / GRPG_TILE;
-    const uint32_t tile = blockIdx.y * tiles_x + blockIdx.x;
-    const int bx0 = blockIdx.x * GRPG_TILE + (warp & 1) * 8;
-    const int wy0 = (warp >> 1) * 8;
+    const int sub = NW == 4 ? warp : (int)(blockIdx.x & 3u);  // NW == 1: one single-warp CTA per 8x8 block, see blend_fwd.cu
+    const uint32_t tile_x = NW == 4 ? blockIdx.x : (blockIdx.x >> 2);
+    const uint32_t tile = blockIdx.y * tiles_x + tile_x;
+    const int bx0 = (int)tile_x * GRPG_TILE + (sub & 1) * 8;
+    const int wy0 = (sub >> 1) * 8;
     const int by0 = (blockIdx.y * row_stride + row_phase) * GRPG_TILE + wy0;
     const int pix_x = bx0 + (lane & 7);
     const int row0 = by0 + 2 * (lane >> 3);
@@ -770,16 +772,16 @@ __global__ void __launch_bounds__(128, MINB) blend_bwd_pipe_kernel(
     uint32_t id_next[RPT];
     fetch_id(tile_last, id_next);
     stage(0, tile_last, id_next);
-    fetch_id(tile_last - BWD_BATCH, id_next);
+    fetch_id(tile_last - BATCH, id_next);
 
-    for (int top = tile_last, it = 0; top > 0; top -= BWD_BATCH, ++it) {
-        const int cnt = min(BWD_BATCH, top);
+    for (int top = tile_last, it = 0; top > 0; top -= BATCH, ++it) {
+        const int cnt = min(BATCH, top);
         cp_async_wait_all();
         __syncthreads();
         const float4* s_rec = s_rec2[it & 1];
         const uint32_t* s_id = s_id2[it & 1];
-        stage((it + 1) & 1, top - BWD_BATCH, id_next);
-        fetch_id(top - 2 * BWD_BATCH, id_next);
+        stage((it + 1) & 1, top - BATCH, id_next);
+        fetch_id(top - 2 * BATCH, id_next);
         if (wmax <= top - cnt) continue;
 
         uint16_t* q = s_q[warp];
@@ -827,7 +829,9 @@ __global__ void __launch_bounds__(128, MINB) blend_bwd_pipe_kernel(
                 Ge[e] = f2(ac0 ? G.x : 0.0f, ac1 ? G.y : 0.0f);
                 any_active[e] = __any_sync(0xffffffffu, ac0 || ac1);
             }
-            // stage B: recurrence + reduction, entry by entry (back to front), one basic block
+            // stage B: recurrence + reduction, entry by entry (back to front), one basic block: the REDs (a branch each)
+            // follow after the last butterfly
+            float mine[NB];
 #pragma unroll
             for (int e = 0; e < NB; ++e) {
                 const float2 om = fadd2(f2(-ae[e].x, -ae[e].y), f2(1.0f));
@@ -863,9 +867,11 @@ __global__ void __launch_bounds__(128, MINB) blend_bwd_pipe_kernel(
                 vals[9] = w2.x + w2.y;
                 vals[10] = wd.x + wd.y;
                 vals[11] = fabsf(py_.x) + fabsf(py_.y);
-                const float mine = warp_reduce12_packed(vals, lane) * slot_scale;
-                if (red_lane && any_active[e]) atomicAdd(grad_rec + (size_t)gid[e] * GREC + red_comp, mine);
+                mine[e] = warp_reduce12_packed(vals, lane) * slot_scale;
             }
+#pragma unroll
+            for (int e = 0; e < NB; ++e)
+                if (red_lane && any_active[e]) atomicAdd(grad_rec + (size_t)gid[e] * GREC + red_comp, mine[e]);
         }
     }
     cp_async_wait_all();
@@ -883,7 +889,7 @@ static int bwd_pixels_per_lane() {
 }
 // GRPG_BWD_PIPE: 0 = blend_bwd_packed_kernel always, 1 = the batched kernel always, 2 = the batched kernel for
 // tile-row bands only (sharded frames); GRPG_BWD_PIPE_CFG = "<min blocks><entries per batch>" (42, 52, 62, 44)
-#define GRPG_BWD_PIPE_DEFAULT 0
+#define GRPG_BWD_PIPE_DEFAULT 2  // bands: 0.238 -> 0.207 ms (band of 8), 0.313 -> 0.292 (of 4), 0.439 -> 0.426 (of 2); whole frame: no gain
 #define GRPG_BWD_PIPE_CFG_DEFAULT 52
 int blend_split_mode();  // blend_fwd.cu
 static int bwd_pipe_mode() {
@@ -938,6 +944,11 @@ void launch_blend_bwd(const grpg_backward_args* a, const uint2* ranges, const ui
     blend_bwd_pipe_kernel<MINBV, NBV><<<grid, 128, 0, stream>>>(ranges, point_list, rec, a->width, a->height, a->background, \
                                                                 a->alphas, n_contrib, a->dL_dpix, a->dL_dpix_depth,        \
                                                                 a->dL_dalphas, grad_rec, HL, stride, phase, gfull)
+        if (blend_split_mode() == 1 || (blend_split_mode() == 2 && stride > 1)) {
+            blend_bwd_pipe_kernel<24, 2, 1, 64><<<dim3(grid.x * 4, grid.y, 1), 32, 0, stream>>>(
+                ranges, point_list, rec, a->width, a->height, a->background, a->alphas, n_contrib, a->dL_dpix,
+                a->dL_dpix_depth, a->dL_dalphas, grad_rec, HL, stride, phase, gfull);
+        } else
         switch (bwd_pipe_cfg()) {
             case 42: GRPG_BWD_PIPE(4, 2); break;
             case 62: GRPG_BWD_PIPE(6, 2); break;

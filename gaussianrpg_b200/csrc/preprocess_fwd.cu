@@ -336,12 +336,6 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
             if (!forward_only) clamped[idx] = (uint8_t)cmask;
         }
         const float opacity = opacities[idx];
-        float hx, hy, thr;
-        alpha_footprint(o.conx, o.cony, o.conz, opacity, o.radius, hx, hy, thr);
-        r.a = make_float4(o.px, o.py, pack_extents(hx, hy), thr);
-        r.b = make_float4(o.conx, o.cony, o.conz, opacity);
-        r.c = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
-        radii[idx] = o.radius;
         // rows of [y0, y1) owned by this band (row % stride == phase), expressed as local row indices
         auto band_clip = [&](uint32_t y0, uint32_t y1, uint32_t& l0, uint32_t& l1) {
             l0 = y0; l1 = y1;
@@ -355,6 +349,15 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
         uint32_t ly0, ly1;
         band_clip(o.ymin, o.ymax, ly0, ly1);
         ref_count = (o.xmax - o.xmin) * (ly1 - ly0);  // what the reference bins: getRect of the 3-sigma radius
+        // A Gaussian whose rectangle has no row in this rank's band emits no instance here, so its record is never
+        // staged: the alpha footprint (double-precision log and square roots, the most expensive part of this kernel)
+        // is skipped for it -- four in five visible Gaussians on a rank of an 8-way sharded frame.
+        float hx = __int_as_float(0x7f800000), hy = hx, thr = -hx;
+        if (ly1 > ly0) alpha_footprint(o.conx, o.cony, o.conz, opacity, o.radius, hx, hy, thr);
+        r.a = make_float4(o.px, o.py, pack_extents(hx, hy), thr);
+        r.b = make_float4(o.conx, o.cony, o.conz, opacity);
+        r.c = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
+        radii[idx] = o.radius;
         uint32_t bx0 = o.xmin, bx1 = o.xmax;
         if (reference_binning != 1 && !(hx == __int_as_float(0x7f800000))) {
             // Clip the rectangle to the tiles that hold a pixel with |dx| <= hx and |dy| <= hy: outside, alpha is

@@ -103,7 +103,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 // ---- one onesweep digit pass -----------------------------------------------------------
-template <bool COMPACT>  // COMPACT: pass 0 of a compacting sort (keep_src given); false removes that code entirely
+template <bool COMPACT, int NBAL = 8>  // COMPACT: pass 0 of a compacting sort (keep_src given); false removes that code
+                                        // entirely.  NBAL: ballots per key = digit bits covered (7 for the 14-bit tile sort)
 __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift, int bits,
@@ -163,8 +164,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) onesweep_pass_kernel(
         const bool kept = !COMPACT || ((keep_bits >> i) & 1u);
         uint32_t peers = COMPACT ? __ballot_sync(0xffffffffu, kept) : 0xffffffffu;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const bool bit = (d >> b) & 1u;  // (a `b < bits` guard was measured slower than the 8 fixed ballots)
+        for (int b = 0; b < NBAL; ++b) {
+            const bool bit = (d >> b) & 1u;  // (a run-time `b < bits` guard was measured slower than fixed ballots)
             const uint32_t bal = __ballot_sync(0xffffffffu, bit);
             peers &= bit ? bal : ~bal;
         }
@@ -366,6 +367,11 @@ static inline bool onesweep_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint3
                 ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
                 iota_values ? 1 : 0, /*precomputed_offsets=*/1, last ? gather_src : nullptr, last ? gather_dst : nullptr,
                 n_dev, keep_src, n_kept_out);
+        else if (plan.bits[p] <= 7)
+            onesweep_pass_kernel<false, 7><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
+                ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
+                (iota_values && p == 0) ? 1 : 0, /*precomputed_offsets=*/1, last ? gather_src : nullptr,
+                last ? gather_dst : nullptr, (keep_src && p > 0) ? n_kept_out : n_dev, nullptr, nullptr);
         else
             onesweep_pass_kernel<false><<<(unsigned)tiles, SORT_THREADS, 0, stream>>>(
                 ki, vi, ko, vo, (uint32_t)n, plan.shift[p], plan.bits[p], hist + p * 256, counters + p, tile_offsets,
