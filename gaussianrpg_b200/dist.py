@@ -532,7 +532,7 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
             graph.replay()
             torch.cuda.synchronize()
             _C.check_static_binning()
-            graph_note = "one CUDA graph per rank: every kernel of forward + loss + backward and the NCCL reduce-scatter"
+            graph_note = "one CUDA graph per rank: every kernel of forward + loss + backward and the record exchange"
         except Exception as exc:  # capture of the collective is the fragile part: fall back to eager launches
             graph = None
             graph_note = f"eager (graph capture failed: {exc!r})"[:300]
@@ -671,8 +671,8 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
                      "algorithmic_bytes_per_launch": alg[dom],
                      "note": f"rank {rank}'s share: R_band={band_R_ref} instances ({band_parsed_R} binned), V_band={band_V}"},
         "parity": parity,
-        "tile_load": dict(tile_load, note="instances per 16x16 tile of this rank's rows: a tile is blended by ONE CTA front to "
-                                          "back, so the heaviest tile bounds the blend kernels however many GPUs share the frame"),
+        "tile_load": dict(tile_load, note="instances per 16x16 tile of this rank's rows: each of its 8x8 blocks is blended by ONE warp "
+                                          "front to back, so the heaviest tile bounds the blend kernels however many GPUs share the frame"),
         "camera_parallel": {"value": 1000.0 * args.steps * world / ms_solo_fb, "unit": "iters/s",
                             "fwd_fps": 1000.0 * args.steps * world / ms_solo_f, "scaling": "weak",
                             "value_with_gradient_allreduce": 1000.0 * args.steps * world / ms_ddp,
@@ -680,10 +680,13 @@ def bench_sharded(args, sc_cpu, dev, rank: int, world: int) -> dict:
                             "note": f"a batch of {world} cameras (poses 1 m apart), one per GPU, single-GPU operator, no "
                                     f"exchange (the upper bound SURVEY 8e asks to report beside the sharded number)"},
         "config": {"workload": f"street scene {P} Gaussians, {W}x{H}, fwd+bwd, one frame split over {world} GPUs",
-                   "parallelism": f"tile rows interleaved mod {world}; training step: loss on the rank's rows, NCCL "
-                                  f"reduce-scatter of the 48 B per-Gaussian gradient records ({48 * P} B), per-Gaussian "
-                                  f"backward on the rank's P/{world} slice (gradient shards); forward-only: fused peer-store "
-                                  f"all-gather of the frame ({band_bytes} B per rank)",
+                   "parallelism": f"tile rows interleaved mod {world}; training step: loss on the rank's rows, "
+                                  + ("sparse peer-store exchange of the in-band 48 B per-Gaussian gradient records"
+                                     if (SPARSE_RECORD_EXCHANGE and any(v is not None for v in _PeerInbox._cache.values()))
+                                     else f"NCCL reduce-scatter of the 48 B per-Gaussian gradient records ({48 * P} B)")
+                                  + f", per-Gaussian backward on the rank's P/{world} slice (gradient shards); forward-only: "
+                                    f"fused peer-store all-gather of the frame ({band_bytes} B per rank); blend kernels of a band: "
+                                    f"one single-warp CTA per 8x8 block, batched queue entries",
                    "static_binning_capacity": capacity,
                    "l2": "no flush: one step streams > 126 MB per GPU (record table 96 MB + instance lists + images)"},
     }
