@@ -23,12 +23,36 @@ __global__ void __launch_bounds__(256) exchange_pack_kernel(int P, int world, in
                                                             const uint32_t* __restrict__ tiles_touched,
                                                             const float4* __restrict__ grad_rec4, ExPtrs ptrs) {
     __shared__ __align__(16) float4 s_run[8][32 * 3];
+    __shared__ uint32_t s_wcnt[8][2];  // senders per warp for the (at most) two owners a CTA of 256 consecutive ids spans
+    __shared__ uint32_t s_wbase[8][2];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* send_count = reinterpret_cast<uint32_t*>(ptrs.inbox[rank]) + 8;
     const bool in_range = i < (uint32_t)P;
     const int owner = in_range ? (int)(i / slice) : -1;
     bool send = in_range && owner != rank && tiles_touched[i] != 0u;
+    // Slots are allocated per CTA: consecutive CTAs address the same owner, so one atomic per WARP on the owner's
+    // counter serialises all resident warps on one L2 address (62 k same-address atomics at P = 2 M).  A CTA of 256
+    // consecutive ids spans at most two owners when slice >= 256; smaller slices keep the per-warp atomics.
+    const uint32_t c0 = blockIdx.x * blockDim.x;
+    const int o0 = (int)(c0 / slice);
+    const bool cta_alloc = slice >= 256u;
+    if (cta_alloc) {
+        const uint32_t m0 = __ballot_sync(0xffffffffu, send && owner == o0);
+        const uint32_t m1 = __ballot_sync(0xffffffffu, send && owner == o0 + 1);
+        if (lane == 0) { s_wcnt[warp][0] = (uint32_t)__popc(m0); s_wcnt[warp][1] = (uint32_t)__popc(m1); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const int j = threadIdx.x;
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_wcnt[w][j];
+            uint32_t base = tot ? atomicAdd(send_count + o0 + j, tot) : 0u;  // (tot != 0 implies a valid foreign owner)
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { s_wbase[w][j] = base; base += s_wcnt[w][j]; }
+        }
+        __syncthreads();
+    }
     uint32_t todo = __ballot_sync(0xffffffffu, send);
     while (todo) {
         const int leader = __ffs(todo) - 1;
@@ -37,8 +61,12 @@ __global__ void __launch_bounds__(256) exchange_pack_kernel(int P, int world, in
         const uint32_t peers = __ballot_sync(0xffffffffu, mine);
         const int n = __popc(peers);
         uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(send_count + lead_owner, (uint32_t)n);
-        base = __shfl_sync(0xffffffffu, base, leader);
+        if (cta_alloc) {
+            base = s_wbase[warp][lead_owner - o0];
+        } else {
+            if (lane == leader) base = atomicAdd(send_count + lead_owner, (uint32_t)n);
+            base = __shfl_sync(0xffffffffu, base, leader);
+        }
         if (mine) {
             const int k = __popc(peers & ((1u << lane) - 1u));
             const float4 a = grad_rec4[3 * (size_t)i], b = grad_rec4[3 * (size_t)i + 1], c = grad_rec4[3 * (size_t)i + 2];
