@@ -32,8 +32,10 @@ __global__ void __launch_bounds__(256) exchange_pack_kernel(int P, int world, in
     const int owner = in_range ? (int)(i / slice) : -1;
     bool send = in_range && owner != rank && tiles_touched[i] != 0u;
     // Slots are allocated per CTA: consecutive CTAs address the same owner, so one atomic per WARP on the owner's
-    // counter serialises all resident warps on one L2 address (62 k same-address atomics at P = 2 M).  A CTA of 256
-    // consecutive ids spans at most two owners when slice >= 256; smaller slices keep the per-warp atomics.
+    // counter puts all resident warps on one L2 address (62 k same-address atomics at P = 2 M); per CTA it is 8 k.  A
+    // CTA of 256 consecutive ids spans at most two owners when slice >= 256; smaller slices keep the per-warp atomics.
+    // (Measured on 2 GPUs: 0.078 ms either way -- there the kernel is bound by the 29 MB it stores over NVLink; the
+    // 8-GPU case, 14 MB per rank, was not re-measured.)
     const uint32_t c0 = blockIdx.x * blockDim.x;
     const int o0 = (int)(c0 / slice);
     const bool cta_alloc = slice >= 256u;
